@@ -1,0 +1,778 @@
+// ssd_b200.cu -- sm_100a kernels + C ABI of the batched SSD grid-world simulator.
+//
+// Design: one warp owns one env instance for a whole step.
+//   * lanes 0..n-1 ARE the agents during move/rotate, conflict resolution, consume and beams:
+//     collisions, swaps, chains and cycles are resolved with __ballot/__match/__shfl/redux,
+//     keeping the reference's sequential phase structure (map_env.py:477-661);
+//   * lanes are spawn candidates during apple/waste spawning (4 apple points or 2 waste
+//     points per Philox4x32-10 call);
+//   * lanes are pixel quads during the egocentric render: 4 pixels -> one 32-bit store per
+//     colour plane into a shared-memory staging tile that leaves the SM as ONE bulk
+//     asynchronous copy (cp.async.bulk shared->global, SASS UBLKCP) per agent chunk.
+// The env's grid is staged in shared memory for the whole step (compact copy for the logic,
+// zero-padded copy with agents overlaid for the render).  No tensor cores: nothing here is a
+// contraction.  HBM traffic per env-step is the algorithmic 2G + n(3N^2+11)+3 bytes (+ padding).
+//
+// Reference citations are relative to drdh/Homophily-MARL.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "ssd_b200.h"
+
+#ifndef SSD_USE_BULK_STORE
+#define SSD_USE_BULK_STORE 1
+#endif
+
+namespace {
+
+constexpr int kWarps = 4;                 // env instances per CTA
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint16_t kNoPoint = 0xFFFF;
+
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
+
+// Static per-map tables, resident in global memory (read through the L1 read-only path).
+struct MapDev {
+    uint8_t  base_grid[SSD_MAX_CELLS];        // reset grid in cell codes
+    uint16_t apple_pts[SSD_MAX_CELLS + 4];    // row-major, padded to x4 with kNoPoint
+    uint16_t waste_pts[SSD_MAX_CELLS + 4];    // padded to x2
+    uint16_t spawn_pts[SSD_MAX_SPAWN];
+    uint32_t thr_apple[SSD_MAX_CELLS + 1];
+    uint32_t thr_waste[SSD_MAX_CELLS + 1];
+};
+
+struct KParams {
+    int kind, B, n, H, W, G, V, N, NN;
+    int GS, NA, PS, AS, ES, PW, PH, PMS;      // strides (ssd_layout) + padded-map geometry
+    int episode_limit, fire_cost, hit_penalty, beam_len, n_actions;
+    int n_apple, n_waste, n_spawn, n_apple4, n_waste2;
+    int random_spawn, spawn_rot;
+    int chunk, smem_per_warp, off_ovl, off_pmap, off_stage;
+    uint32_t invN20, invW20;                  // floor(x / N) == (x * invN20) >> 20 on the used ranges
+    uint32_t seed_lo, seed_hi, gid_base;
+    uint32_t thr_harvest[4];
+    uint32_t lut[16];
+    const MapDev* map;
+    uint8_t* grid; uint32_t* agent; int32_t* ep_ret; int32_t* t; uint32_t* tick;
+    const uint8_t* actions; const uint8_t* mask;
+    int8_t* reward; uint8_t* clean; uint16_t* apple_cnt; uint8_t* done; uint8_t* obs; uint8_t* state_rgb;
+    const uint32_t* d_prio; const uint32_t* d_uapple; const uint32_t* d_uwaste; const uint32_t* d_wkey;
+    const uint32_t* d_spawnkey; const uint8_t* d_rot;
+};
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint32_t pick(const uint4& v, int i) {
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+// draw streams: 0 mover priority, 1 apple, 2 waste (u, order key), 3 spawn key, 4 spawn rotation
+__device__ __forceinline__ uint32_t philox_word(const KParams& p, uint32_t gid, uint32_t tick, uint32_t stream, uint32_t idx) {
+    const uint4 r = philox4x32_10(gid, tick, stream, idx >> 2, p.seed_lo, p.seed_hi);
+    return pick(r, idx & 3);
+}
+
+// agent i is drawn as the first char of str(i % 10 + 1)  (map_env.py:370 into a <U1 array)
+__device__ __forceinline__ int agent_colour_index(int i) {
+    const int v = i % 10 + 1;
+    return 6 + (v == 10 ? 1 : v);
+}
+
+// ------------------------------------------------------------------ update_moves (map_env.py:477-661)
+// lanes < n hold one agent each: pos (cell index), ori, act.  Non-agent lanes carry unique
+// negative positions so they never match a cell.
+__device__ __forceinline__ void update_moves(const KParams& p, const uint8_t* __restrict__ sg, int lane, bool is_agent,
+                                             int act, int& pos, int& ori, int env, uint32_t gid, uint32_t tick) {
+    // turns take effect immediately (map_env.py:509-511, 843-861)
+    if (act == 5) ori = (0x0132 >> (4 * ori)) & 3;           // CW : LEFT->UP, RIGHT->DOWN, UP->RIGHT, DOWN->LEFT
+    else if (act == 6) ori = (0x1023 >> (4 * ori)) & 3;      // CCW: LEFT->DOWN, RIGHT->UP, UP->LEFT, DOWN->RIGHT
+    const bool mover = is_agent && act <= 4;
+    int prop = pos;
+    if (mover && act < 4) {
+        // (drow, dcol) of action a under orientation o, 2-bit fields holding value+1 (map_env.py:826-835)
+        //   LEFT : (0,+1) (0,-1) (-1,0) (+1,0)   RIGHT: (0,-1) (0,+1) (+1,0) (-1,0)
+        //   UP   : (-1,0) (+1,0) (0,-1) (0,+1)   DOWN : (+1,0) (-1,0) (0,+1) (0,-1)
+        constexpr uint32_t kDr = (1u) | (1u << 2) | (0u << 4) | (2u << 6) | (1u << 8) | (1u << 10) | (2u << 12) | (0u << 14) |
+                                 (0u << 16) | (2u << 18) | (1u << 20) | (1u << 22) | (2u << 24) | (0u << 26) | (1u << 28) | (1u << 30);
+        constexpr uint32_t kDc = (2u) | (0u << 2) | (1u << 4) | (1u << 6) | (0u << 8) | (2u << 10) | (1u << 12) | (1u << 14) |
+                                 (1u << 16) | (1u << 18) | (0u << 20) | (2u << 22) | (1u << 24) | (1u << 26) | (2u << 28) | (0u << 30);
+        const int f = 2 * (ori * 4 + act);
+        const int dr = (int)((kDr >> f) & 3u) - 1, dc = (int)((kDc >> f) & 3u) - 1;
+        const int q = pos + dr * p.W + dc;
+        prop = sg[q] == SSD_CELL_WALL ? pos : q;             // agent.py:111-119
+    }
+    unsigned in_moves = __ballot_sync(kFull, mover);
+    if (in_moves == 0) return;                                // map_env.py:534
+    int mv = prop;                                            // live agent_moves[i]
+
+    // ---- phase 1: contested cells in lexicographic order of the ORIGINAL proposals (543-609)
+    const unsigned grp = __match_any_sync(kFull, mover ? prop : -1000 - lane);
+    unsigned pending = __ballot_sync(kFull, mover && __popc(grp) >= 2);
+    if (pending) {
+        uint32_t prio = 0;
+        if (mover) prio = p.d_prio ? p.d_prio[(size_t)env * p.n + lane] : philox_word(p, gid, tick, 0, (uint32_t)lane);
+        while (pending) {
+            const int cell = __reduce_min_sync(kFull, ((pending >> lane) & 1u) ? prop : 0x7fffffff);
+            const bool in_cont = mover && prop == cell;
+            const unsigned cont = __ballot_sync(kFull, in_cont);
+            const unsigned occm = __ballot_sync(kFull, pos == cell);          // live positions (567)
+            bool free_cell = true;
+            if (occm) {
+                const int occ = 31 - __clz(occm);                              // dict build: last index wins (516)
+                const int mv_occ = __shfl_sync(kFull, mv, occ);
+                const bool occ_moves = (in_moves >> occ) & 1u;
+                const bool c1 = (cont >> occ) & 1u;                            // (1) 578
+                const bool c2 = !occ_moves || mv_occ == cell;                  // (2) 584-586
+                const unsigned swp = __ballot_sync(kFull, in_cont && mv_occ == pos);   // (3) 590-594
+                free_cell = !(c1 || c2 || swp != 0);
+            }
+            if (free_cell) {                                                   // winner = first in shuffled order (598-601)
+                const uint32_t mk = __reduce_min_sync(kFull, in_cont ? prio : 0xffffffffu);
+                const unsigned eq = __ballot_sync(kFull, in_cont && prio == mk);
+                if (lane == __ffs(eq) - 1) pos = cell;
+            }
+            if (in_cont) mv = pos;                                             // 604-609
+            pending &= ~cont;
+        }
+    }
+    // ---- phase 2: iterate until every move is made or dropped (612-661)
+    while (in_moves) {
+        const int spos = pos;                                  // snapshot dict of this pass (613)
+        const unsigned snap = in_moves;
+        unsigned todo = snap;
+        while (todo) {
+            const int i = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (!((in_moves >> i) & 1u)) continue;             // deleted earlier in this pass (619-620)
+            const int mvi = __shfl_sync(kFull, mv, i);
+            const int posi = __shfl_sync(kFull, pos, i);
+            const unsigned live = __ballot_sync(kFull, pos == mvi);            // 621
+            if (!live) {                                                       // 650-653
+                if (lane == i) pos = mvi;
+                in_moves &= ~(1u << i);
+                continue;
+            }
+            const unsigned sm = __ballot_sync(kFull, spos == mvi);
+            if (!sm) { in_moves &= ~(1u << i); continue; }                     // reference KeyError; unreachable
+            const int occ = 31 - __clz(sm);
+            const int pos_occ = __shfl_sync(kFull, pos, occ);
+            const int mv_occ = __shfl_sync(kFull, mv, occ);
+            const int occ_mv = ((in_moves >> occ) & 1u) ? mv_occ : pos_occ;
+            if (occ == i) in_moves &= ~(1u << i);                                              // (1) 630
+            else if (!((snap >> occ) & 1u) || pos_occ == occ_mv) in_moves &= ~(1u << i);       // (2) 636-639
+            else if (mv_occ == posi && mvi == pos_occ) in_moves &= ~((1u << i) | (1u << occ)); // (3) 642-648
+        }
+        if (in_moves == snap) {                                // nobody could move: rotate cycles together (658-661)
+            if ((in_moves >> lane) & 1u) pos = mv;
+            break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ beams (map_env.py:663-769)
+__device__ __forceinline__ void beams(const KParams& p, uint8_t* sg, const uint8_t* ovl, int lane, bool is_agent,
+                                      int act, int pos, int ori, int& reward, int& clean_num) {
+    const bool fire = is_agent && act == 7;
+    const bool clean = is_agent && act == 8 && p.kind == SSD_KIND_CLEANUP;
+    if (fire) reward -= p.fire_cost;                          // agent.py:188-190, 239-241
+    unsigned need = __ballot_sync(kFull, clean || (fire && p.hit_penalty != 0));
+    while (need) {                                            // agent index order, map effects applied per agent (669-671)
+        const int i = __ffs(need) - 1;
+        need &= need - 1;
+        const int posi = __shfl_sync(kFull, pos, i), orii = __shfl_sync(kFull, ori, i);
+        const bool is_clean = __shfl_sync(kFull, act, i) == 8;
+        // firing direction ORIENTATIONS[o] and its right-hand rotation (map_env.py:28-31, 840-841)
+        const int dr = orii == 0 ? -1 : (orii == 1 ? 1 : 0), dc = orii == 2 ? -1 : (orii == 3 ? 1 : 0);
+        const int rr = orii == 2 ? 1 : (orii == 3 ? -1 : 0), rc = orii == 0 ? -1 : (orii == 1 ? 1 : 0);
+        const int d = dr * p.W + dc, rs = rr * p.W + rc;
+        int upd = -1, hit = -1;
+        if (lane < 3) {                                       // the three parallel rays (728-730)
+            int q = posi + (lane == 0 ? d : (lane == 1 ? rs : -rs));
+            for (int k = 0; k < p.beam_len; ++k) {            // maps are wall-enclosed: a ray cannot leave the map
+                const int code = sg[q];
+                if (code == SSD_CELL_WALL) break;             // 737
+                const int o = ovl[q];
+                if (o) {                                      // agents absorb beams (741-749)
+                    if (!is_clean) hit = o - 1;
+                    if (is_clean && code == SSD_CELL_WASTE) upd = q;
+                    break;
+                }
+                if (is_clean && code == SSD_CELL_WASTE) { upd = q; break; }   // 752-760
+                q += d;
+            }
+        }
+        __syncwarp();
+        if (upd >= 0) sg[upd] = SSD_CELL_RIVER;
+        __syncwarp();
+        const unsigned um = __ballot_sync(kFull, upd >= 0);
+        if (lane == i && is_clean) clean_num = __popc(um);    // 672-673
+        if (p.hit_penalty != 0) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) if (__shfl_sync(kFull, hit, s) == lane) reward -= p.hit_penalty;   // agent.py:184-186
+        }
+    }
+}
+
+// ------------------------------------------------------------------ spawning (cleanup.py:165-204, harvest.py:92-122)
+__device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, const uint8_t* ovl, int lane, int env,
+                                      uint32_t gid, uint32_t tick) {
+    const MapDev* __restrict__ m = p.map;
+    uint32_t tA = 1, tW = 0;
+    if (p.kind == SSD_KIND_CLEANUP) {
+        int h = 0;                                            // compute_permitted_area: count 'H'
+        for (int i = lane; i < (p.GS >> 2); i += 32)
+            h += __popc(__vcmpeq4(reinterpret_cast<const uint32_t*>(sg)[i], 0x03030303u)) >> 3;
+        h = __reduce_add_sync(kFull, h);
+        tA = __ldg(&m->thr_apple[h]);
+        tW = __ldg(&m->thr_waste[h]);
+    }
+    // apples: 4 candidate points per lane per Philox call; decisions use the pre-spawn grid
+    unsigned long long decided = 0;
+    if (tA != 0) {
+        int it = 0;
+        for (int j = lane; j < p.n_apple4; j += 32, ++it) {
+            const ushort4 pts = __ldg(reinterpret_cast<const ushort4*>(m->apple_pts) + j);
+            const uint16_t c4[4] = { pts.x, pts.y, pts.z, pts.w };
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (!p.d_uapple) r = philox4x32_10(gid, tick, 1u, (uint32_t)j, p.seed_lo, p.seed_hi);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = c4[q];
+                if (c == kNoPoint) continue;
+                if (ovl[c] != 0 || sg[c] == SSD_CELL_APPLE) continue;          // cleanup.py:171, harvest.py:105
+                uint32_t thr = tA;
+                if (p.kind == SSD_KIND_HARVEST) {
+                    int cnt = 0;                                               // j^2+k^2 <= 2: the 3x3 block (harvest.py:107-116)
+#pragma unroll
+                    for (int a = -1; a <= 1; ++a)
+#pragma unroll
+                        for (int b = -1; b <= 1; ++b) cnt += sg[c + a * p.W + b] == SSD_CELL_APPLE;
+                    thr = p.thr_harvest[cnt < 3 ? cnt : 3];
+                }
+                const uint32_t u = p.d_uapple ? p.d_uapple[(size_t)env * p.G + c] : pick(r, q);
+                if (u < thr) decided |= 1ull << (it * 4 + q);
+            }
+        }
+    }
+    // waste: visit eligible waste points in ascending (order key, cell); the first success spawns one 'H'
+    int wcell = -1;
+    if (tW != 0) {
+        uint32_t bk = 0xffffffffu, bc = 0xffffffffu;
+        for (int j = lane; j < p.n_waste2; j += 32) {
+            const ushort2 pts = __ldg(reinterpret_cast<const ushort2*>(m->waste_pts) + j);
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (!p.d_uwaste) r = philox4x32_10(gid, tick, 2u, (uint32_t)j, p.seed_lo, p.seed_hi);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t c = q ? pts.y : pts.x;
+                if (c == kNoPoint || sg[c] == SSD_CELL_WASTE) continue;        // cleanup.py:182
+                const uint32_t u = p.d_uwaste ? p.d_uwaste[(size_t)env * p.G + c] : (q ? r.z : r.x);
+                const uint32_t key = p.d_uwaste ? p.d_wkey[(size_t)env * p.G + c] : (q ? r.w : r.y);
+                if (u < tW && (key < bk || (key == bk && c < bc))) { bk = key; bc = c; }
+            }
+        }
+        const bool have = bc != 0xffffffffu;
+        if (__ballot_sync(kFull, have)) {
+            const uint32_t mk = __reduce_min_sync(kFull, have ? bk : 0xffffffffu);
+            wcell = (int)__reduce_min_sync(kFull, (have && bk == mk) ? bc : 0xffffffffu);
+        }
+    }
+    __syncwarp();                                             // every decision read the pre-spawn grid
+    if (decided) {
+        int it = 0;
+        for (int j = lane; j < p.n_apple4; j += 32, ++it) {
+            const ushort4 pts = __ldg(reinterpret_cast<const ushort4*>(m->apple_pts) + j);
+            const uint16_t c4[4] = { pts.x, pts.y, pts.z, pts.w };
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if ((decided >> (it * 4 + q)) & 1ull) sg[c4[q]] = SSD_CELL_APPLE;
+        }
+    }
+    if (wcell >= 0 && lane == 0) sg[wcell] = SSD_CELL_WASTE;
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ render (map_env.py:360-379, 418-446, 795-815, 923-957)
+__device__ __forceinline__ void bulk_store_wait_read() {
+#if SSD_USE_BULK_STORE
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+
+__device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint8_t* pmap, uint8_t* stage,
+                                       const uint32_t* lut_s, int lane, bool is_agent, int pos, int ori, int env) {
+    // zero-padded copy of the map in colour indices, agents overlaid (utility_funcs.py:58-116 without np.pad)
+    for (int i = lane; i < (p.PMS >> 4); i += 32)
+        reinterpret_cast<uint4*>(pmap)[i] = make_uint4(0x06060606u, 0x06060606u, 0x06060606u, 0x06060606u);
+    __syncwarp();
+    for (int c = lane; c < p.G; c += 32) {
+        const int r = (int)(((uint32_t)c * p.invW20) >> 20);
+        pmap[(r + p.V) * p.PW + (c - r * p.W) + p.V] = sg[c];
+    }
+    int ppos = 0;
+    if (is_agent) {
+        const int r = (int)(((uint32_t)pos * p.invW20) >> 20);
+        ppos = (r + p.V) * p.PW + (pos - r * p.W) + p.V;
+    }
+    __syncwarp();
+    const unsigned same = __match_any_sync(kFull, pos);
+    if (is_agent && lane == 31 - __clz(same)) pmap[ppos] = (uint8_t)agent_colour_index(lane);   // later index overwrites (370)
+    __syncwarp();
+
+    if (p.state_rgb) {                                        // get_state: unrotated full map (950-957)
+        uint8_t* out = p.state_rgb + (size_t)env * 3 * p.G;
+        for (int c = lane; c < p.G; c += 32) {
+            const int r = (int)(((uint32_t)c * p.invW20) >> 20);
+            const uint32_t rgb = lut_s[pmap[(r + p.V) * p.PW + (c - r * p.W) + p.V]];
+            out[c] = (uint8_t)rgb; out[p.G + c] = (uint8_t)(rgb >> 8); out[2 * p.G + c] = (uint8_t)(rgb >> 16);
+        }
+    }
+    if (!p.obs) return;
+
+    const int quads = p.PS >> 2;
+    const int tail = p.AS - 3 * p.PS;                         // 0..12 pad bytes per agent block
+    for (int a0 = 0; a0 < p.n; a0 += p.chunk) {
+        const int ka = min(p.chunk, p.n - a0);
+        if (a0 > 0) { if (lane == 0) bulk_store_wait_read(); __syncwarp(); }   // staging tile is being re-used
+        for (int al = 0; al < ka; ++al) {
+            const int a = a0 + al;
+            const int base = __shfl_sync(kFull, ppos, a);
+            const int o = __shfl_sync(kFull, ori, a);
+            // source = base + A*y + B*x + C   (np.rot90 k = 1, 3, 0, 2 for LEFT, RIGHT, UP, DOWN; 806-813)
+            int A, Bc, C;
+            if (o == 2)      { A = p.PW;  Bc = 1;     C = -p.V * p.PW - p.V; }
+            else if (o == 0) { A = -1;    Bc = p.PW;  C = -p.V * p.PW + p.V; }
+            else if (o == 3) { A = -p.PW; Bc = -1;    C = p.V * p.PW + p.V; }
+            else             { A = 1;     Bc = -p.PW; C = p.V * p.PW - p.V; }
+            const int wrap = A - p.N * Bc;
+            uint8_t* dst = stage + al * p.AS;
+            for (int q = lane; q < quads; q += 32) {
+                const int p0 = q << 2;
+                int y = (int)(((uint32_t)p0 * p.invN20) >> 20);
+                int x = p0 - y * p.N;
+                int src = base + C + A * y + Bc * x;
+                uint32_t px[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    px[k] = (p0 + k < p.NN) ? lut_s[pmap[src]] : 0u;
+                    src += Bc;
+                    if (++x == p.N) { x = 0; src += wrap; }
+                }
+                const uint32_t lo = __byte_perm(px[0], px[1], 0x5140), hi = __byte_perm(px[2], px[3], 0x5140);
+                const uint32_t lb = __byte_perm(px[0], px[1], 0x0062), hb = __byte_perm(px[2], px[3], 0x0062);
+                *reinterpret_cast<uint32_t*>(dst + p0) = __byte_perm(lo, hi, 0x5410);
+                *reinterpret_cast<uint32_t*>(dst + p.PS + p0) = __byte_perm(lo, hi, 0x7632);
+                *reinterpret_cast<uint32_t*>(dst + 2 * p.PS + p0) = __byte_perm(lb, hb, 0x5410);
+            }
+            if (lane < (tail >> 2)) *reinterpret_cast<uint32_t*>(dst + 3 * p.PS + 4 * lane) = 0u;
+        }
+        uint8_t* gdst = p.obs + (size_t)env * p.ES + (size_t)a0 * p.AS;
+        const int bytes = ka * p.AS;
+#if SSD_USE_BULK_STORE
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#else
+        __syncwarp();
+        for (int i = lane; i < (bytes >> 4); i += 32)
+            reinterpret_cast<uint4*>(gdst)[i] = reinterpret_cast<const uint4*>(stage)[i];
+#endif
+    }
+    if (lane == 0) bulk_store_wait_read();                    // smem must outlive the async reads
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int MODE>
+__global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t lut_s[16];
+    if (threadIdx.x < 16) lut_s[threadIdx.x] = p.lut[threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * kWarps + warp;
+    if (env >= p.B) return;
+    if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
+
+    uint8_t* sg = smem + (size_t)warp * p.smem_per_warp;
+    uint8_t* ovl = sg + p.off_ovl;
+    uint8_t* pmap = sg + p.off_pmap;
+    uint8_t* stage = sg + p.off_stage;
+    const bool is_agent = lane < p.n;
+    const uint32_t gid = p.gid_base + (uint32_t)env;
+    uint32_t tick = p.tick[env];
+    int pos = -1 - lane, ori = 0, ep_ret = 0;
+
+    // zero the agent-occupancy tile, stage the grid
+    for (int i = lane; i < (p.GS >> 4); i += 32) reinterpret_cast<uint4*>(ovl)[i] = make_uint4(0, 0, 0, 0);
+    if (MODE == MODE_RESET) {
+        for (int i = lane; i < (p.GS >> 4); i += 32)
+            reinterpret_cast<uint4*>(sg)[i] = __ldg(reinterpret_cast<const uint4*>(p.map->base_grid) + i);
+    } else {
+        const uint4* src = reinterpret_cast<const uint4*>(p.grid + (size_t)env * p.GS);
+        for (int i = lane; i < (p.GS >> 4); i += 32) reinterpret_cast<uint4*>(sg)[i] = src[i];
+        if (is_agent) {
+            const uint32_t a = p.agent[(size_t)env * p.NA + lane];
+            pos = (int)(a & 0xff) * p.W + (int)((a >> 8) & 0xff);
+            ori = (int)((a >> 16) & 3);
+            ep_ret = p.ep_ret[(size_t)env * p.NA + lane];
+        }
+    }
+    __syncwarp();
+
+    if (MODE == MODE_STEP) {
+        const int act = is_agent ? (int)p.actions[(size_t)env * p.n + lane] : 255;
+        int reward = 0, clean_num = 0;
+        update_moves(p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
+        // consume in index order: the lowest index on a cell eats the apple (253-256)
+        const unsigned same = __match_any_sync(kFull, pos);
+        const bool eats = is_agent && sg[pos < 0 ? 0 : pos] == SSD_CELL_APPLE && lane == __ffs(same) - 1;
+        if (is_agent && lane == 31 - __clz(same)) ovl[pos] = (uint8_t)(lane + 1);           // dict: last index wins
+        __syncwarp();
+        if (eats) { reward += 1; sg[pos] = SSD_CELL_EMPTY; }
+        __syncwarp();
+        beams(p, sg, ovl, lane, is_agent, act, pos, ori, reward, clean_num);                // 259-260
+        spawn(p, sg, ovl, lane, env, gid, tick);                                            // 263
+        // apple density numerator (291-292): after consume + spawn no apple lies under an agent
+        int apples = 0;
+        for (int i = lane; i < (p.GS >> 2); i += 32)
+            apples += __popc(__vcmpeq4(reinterpret_cast<const uint32_t*>(sg)[i], 0x02020202u)) >> 3;
+        apples = __reduce_add_sync(kFull, apples);
+        const int t = p.t[env] + 1;
+        if (is_agent) {
+            p.reward[(size_t)env * p.n + lane] = (int8_t)reward;
+            p.clean[(size_t)env * p.n + lane] = (uint8_t)clean_num;
+            ep_ret += reward;                                                               // 885-888
+        }
+        if (lane == 0) {
+            p.apple_cnt[env] = (uint16_t)apples;
+            p.done[env] = t >= p.episode_limit;                                             // 890-894
+            p.t[env] = t;
+            p.tick[env] = tick + 1;
+        }
+    } else if (MODE == MODE_RESET) {
+        // setup_agents: agent i takes the free spawn point with the largest (key, cell) (map_env.py:771-784)
+        const bool is_sp = lane < p.n_spawn;
+        const int mycell = is_sp ? (int)__ldg(&p.map->spawn_pts[lane]) : -1;
+        bool taken = false;
+        for (int i = 0; i < p.n; ++i) {
+            uint32_t key = 0;
+            if (p.random_spawn && is_sp)
+                key = p.d_spawnkey ? p.d_spawnkey[((size_t)env * p.n + i) * p.G + mycell]
+                                   : philox_word(p, gid, tick, 3u, (uint32_t)(i * p.n_spawn + lane));
+            const bool cand = is_sp && !taken;
+            const uint32_t mk = __reduce_max_sync(kFull, cand ? key : 0u);
+            const unsigned eq = __ballot_sync(kFull, cand && key == mk);
+            const int w = 31 - __clz(eq);
+            const int cell = __shfl_sync(kFull, mycell, w);
+            if (lane == w) taken = true;
+            if (lane == i) pos = cell;
+        }
+        if (is_agent) {                                                                     // spawn_rotation (786-793)
+            if (p.spawn_rot >= 0) ori = p.spawn_rot;
+            else ori = p.d_rot ? (int)(p.d_rot[(size_t)env * p.n + lane] & 3) : (int)(philox_word(p, gid, tick, 4u, (uint32_t)lane) >> 30);
+        }
+        const unsigned same = __match_any_sync(kFull, pos);
+        if (is_agent && lane == 31 - __clz(same)) ovl[pos] = (uint8_t)(lane + 1);
+        __syncwarp();
+        spawn(p, sg, ovl, lane, env, gid, tick);                                            // custom_map_update (313)
+        ep_ret = 0;
+        if (lane == 0) { p.t[env] = 0; p.tick[env] = tick + 1; }
+    }
+
+    if (MODE != MODE_RENDER) {                                 // write the state back
+        uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * p.GS);
+        for (int i = lane; i < (p.GS >> 4); i += 32) dst[i] = reinterpret_cast<const uint4*>(sg)[i];
+        if (is_agent) {
+            const int r = (int)(((uint32_t)pos * p.invW20) >> 20);
+            p.agent[(size_t)env * p.NA + lane] = (uint32_t)r | ((uint32_t)(pos - r * p.W) << 8) | ((uint32_t)ori << 16);
+            p.ep_ret[(size_t)env * p.NA + lane] = ep_ret;
+        }
+    }
+    if (p.obs || p.state_rgb) render(p, sg, pmap, stage, lut_s, lane, is_agent, pos, ori, env);
+}
+
+// ------------------------------------------------------------------ incentive bookkeeping (homophily_learner.py:98-115)
+__global__ void incentive_kernel(const long long* __restrict__ a_inc, const float* __restrict__ reward, long long rows, int n,
+                                 float incentive, float cost, float ratio, float T, int recip,
+                                 float* __restrict__ r_env, float* __restrict__ r_inc, float* __restrict__ sgn) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * n) return;
+    const long long row = idx / n;
+    const int k = (int)(idx - row * n);
+    const long long* a = a_inc + row * n * n;
+    int give = 0, rp = 0, rn = 0;
+    for (int j = 0; j < n; ++j) {
+        if (j == k) continue;                                  // inc_mask_actions = 1 - eye
+        give += a[k * n + j] != 0;
+        const long long v = a[j * n + k];
+        rp += v == 1; rn += v == 2;
+    }
+    const float rv = (float)(rp - rn), r = reward[idx];
+    const float e = __fadd_rn(r, __fmul_rn(__fmul_rn(rv, ratio), incentive));
+    const float c = __fsub_rn(r, __fmul_rn(__fmul_rn((float)give, cost), incentive));
+    if (recip) { const float inv = __fdiv_rn(1.0f, T); r_env[idx] = __fmul_rn(e, inv); r_inc[idx] = __fmul_rn(c, inv); }
+    else { r_env[idx] = __fdiv_rn(e, T); r_inc[idx] = __fdiv_rn(c, T); }
+    if (sgn) sgn[idx] = rv > 0.f ? 1.f : (rv < 0.f ? -1.f : 0.f);
+}
+
+thread_local int g_last_cuda_error = 0;
+
+inline int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return SSD_ERR_CUDA; }
+#define SSD_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+uint32_t magic20(int d, int max_x) {
+    // smallest m with floor(x*m / 2^20) == floor(x / d) for all 0 <= x <= max_x (verified exhaustively)
+    uint32_t m = (uint32_t)(((1u << 20) + d - 1) / d);
+    for (int x = 0; x <= max_x; ++x)
+        if ((int)(((uint64_t)x * m) >> 20) != x / d) return 0;
+    return m;
+}
+
+}  // namespace
+
+struct ssd_handle {
+    KParams kp;
+    MapDev* d_map;
+    int device;
+    size_t smem_bytes;
+    int64_t launches;
+};
+
+static int fill_common(const ssd_handle* h, const ssd_state* st, const ssd_draws* d, KParams& k) {
+    if (!h || !st || !st->grid || !st->agent || !st->ep_ret || !st->t || !st->tick) return SSD_ERR_INVALID;
+    k = h->kp;
+    k.grid = st->grid; k.agent = st->agent; k.ep_ret = st->ep_ret; k.t = st->t; k.tick = st->tick;
+    if (d) {
+        if ((d->u_waste == nullptr) != (d->wkey == nullptr)) return SSD_ERR_INVALID;
+        k.d_prio = d->prio; k.d_uapple = d->u_apple; k.d_uwaste = d->u_waste; k.d_wkey = d->wkey;
+        k.d_spawnkey = d->spawn_key; k.d_rot = d->rot;
+    }
+    return SSD_OK;
+}
+
+template <int MODE>
+static int launch(ssd_handle* h, const KParams& k, void* stream) {
+    static size_t max_smem = 0;                               // the attribute is a per-function maximum: only raise it
+    if (h->smem_bytes > max_smem) {
+        SSD_CUDA(cudaFuncSetAttribute(ssd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        max_smem = h->smem_bytes;
+    }
+    const int grid = (k.B + kWarps - 1) / kWarps;
+    ssd_kernel<MODE><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
+    ++h->launches;
+    SSD_CUDA(cudaGetLastError());
+    return SSD_OK;
+}
+
+extern "C" {
+
+int ssd_abi_version(void) { return SSD_B200_ABI_VERSION; }
+
+const char* ssd_error_string(int code) {
+    switch (code) {
+        case SSD_OK: return "ok";
+        case SSD_ERR_INVALID: return "invalid argument or unsupported geometry";
+        case SSD_ERR_CUDA: return "CUDA runtime error";
+        case SSD_ERR_SPAWN: return "There are not enough spawn points! Check your map?";
+        case SSD_ERR_MAP: return "map must be wall-enclosed and use the reference alphabet";
+        default: return "unknown error";
+    }
+}
+
+int ssd_last_cuda_error(void) { return g_last_cuda_error; }
+
+uint32_t ssd_prob_to_threshold(double p) {
+    if (!(p > 0.0)) return 0u;
+    const double t = ceil(p * 4294967296.0);
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
+int ssd_create(const ssd_config* cfg, ssd_handle** out) {
+    if (!cfg || !out || !cfg->ascii_map) return SSD_ERR_INVALID;
+    *out = nullptr;
+    const int H = cfg->height, W = cfg->width, G = H * W, n = cfg->n_agents, V = cfg->view;
+    if (cfg->kind != SSD_KIND_CLEANUP && cfg->kind != SSD_KIND_HARVEST) return SSD_ERR_INVALID;
+    if (H < 3 || W < 3 || H > 255 || W > 255 || G > SSD_MAX_CELLS) return SSD_ERR_INVALID;
+    if (n < 1 || n > SSD_MAX_AGENTS || V < 1 || V > 31 || cfg->n_envs < 1) return SSD_ERR_INVALID;
+    if (cfg->beam_len < 0 || cfg->episode_limit < 1 || cfg->spawn_rotation > 3) return SSD_ERR_INVALID;
+    if (abs(cfg->fire_cost) + n * abs(cfg->hit_penalty) + 1 > 127) return SSD_ERR_INVALID;   // reward is int8
+
+    MapDev* hm = new (std::nothrow) MapDev;
+    if (!hm) return SSD_ERR_INVALID;
+    memset(hm, 0, sizeof(MapDev));
+    int na = 0, nw = 0, ns = 0;
+    for (int c = 0; c < G; ++c) {
+        const char ch = cfg->ascii_map[c];
+        const int r = c / W, col = c % W;
+        const bool border = r == 0 || col == 0 || r == H - 1 || col == W - 1;
+        if (border && ch != '@') { delete hm; return SSD_ERR_MAP; }
+        uint8_t code = SSD_CELL_EMPTY;
+        switch (ch) {
+            case '@': code = SSD_CELL_WALL; break;
+            case ' ': break;
+            case 'P': if (ns < SSD_MAX_SPAWN) hm->spawn_pts[ns] = (uint16_t)c; ++ns; break;   // map_env.py:143-146
+            case 'A': if (cfg->kind == SSD_KIND_HARVEST) { code = SSD_CELL_APPLE; hm->apple_pts[na++] = (uint16_t)c; } break;
+            case 'B': if (cfg->kind == SSD_KIND_CLEANUP) hm->apple_pts[na++] = (uint16_t)c; break;   // cleanup.py:81-82
+            case 'H': if (cfg->kind == SSD_KIND_CLEANUP) { code = SSD_CELL_WASTE; hm->waste_pts[nw++] = (uint16_t)c; } break;
+            case 'R': if (cfg->kind == SSD_KIND_CLEANUP) code = SSD_CELL_RIVER; break;
+            case 'S': if (cfg->kind == SSD_KIND_CLEANUP) code = SSD_CELL_STREAM; break;
+            default: delete hm; return SSD_ERR_MAP;
+        }
+        hm->base_grid[c] = code;
+    }
+    if (ns < n) { delete hm; return SSD_ERR_SPAWN; }
+    if (ns > SSD_MAX_SPAWN) { delete hm; return SSD_ERR_INVALID; }
+    for (int k = na; k < round_up(na, 4) + 4 && k < SSD_MAX_CELLS + 4; ++k) hm->apple_pts[k] = kNoPoint;
+    for (int k = nw; k < round_up(nw, 2) + 2 && k < SSD_MAX_CELLS + 4; ++k) hm->waste_pts[k] = kNoPoint;
+    if (cfg->kind == SSD_KIND_CLEANUP) {
+        if (cfg->n_waste_lut != (uint32_t)nw + 1 || !cfg->thr_apple || !cfg->thr_waste) { delete hm; return SSD_ERR_INVALID; }
+        memcpy(hm->thr_apple, cfg->thr_apple, sizeof(uint32_t) * (nw + 1));
+        memcpy(hm->thr_waste, cfg->thr_waste, sizeof(uint32_t) * (nw + 1));
+    }
+
+    ssd_handle* h = new (std::nothrow) ssd_handle;
+    if (!h) { delete hm; return SSD_ERR_INVALID; }
+    memset(h, 0, sizeof(*h));
+    KParams& k = h->kp;
+    k.kind = cfg->kind; k.B = cfg->n_envs; k.n = n; k.H = H; k.W = W; k.G = G; k.V = V; k.N = 2 * V + 1; k.NN = k.N * k.N;
+    k.GS = round_up(G, 16); k.NA = round_up(n, 4);
+    k.PS = round_up(k.NN, 4); k.AS = round_up(3 * k.PS, 16); k.ES = n * k.AS;
+    k.PW = W + 2 * V; k.PH = H + 2 * V; k.PMS = round_up(k.PW * k.PH, 16);
+    k.episode_limit = cfg->episode_limit; k.fire_cost = cfg->fire_cost; k.hit_penalty = cfg->hit_penalty;
+    k.beam_len = cfg->beam_len; k.n_actions = cfg->kind == SSD_KIND_CLEANUP ? 9 : 8;
+    k.n_apple = na; k.n_waste = nw; k.n_spawn = ns; k.n_apple4 = (na + 3) / 4; k.n_waste2 = (nw + 1) / 2;
+    k.random_spawn = cfg->random_spawn_point != 0; k.spawn_rot = cfg->spawn_rotation < 0 ? -1 : cfg->spawn_rotation;
+    k.invN20 = magic20(k.N, k.PS + 4); k.invW20 = magic20(W, G + 1);
+    k.seed_lo = (uint32_t)cfg->seed; k.seed_hi = (uint32_t)(cfg->seed >> 32); k.gid_base = cfg->env_gid_base;
+    for (int i = 0; i < 4; ++i) k.thr_harvest[i] = cfg->thr_harvest[i];
+    for (int i = 0; i < 16; ++i)
+        k.lut[i] = (uint32_t)cfg->color_lut[i][0] | ((uint32_t)cfg->color_lut[i][1] << 8) | ((uint32_t)cfg->color_lut[i][2] << 16);
+    if (k.invN20 == 0 || k.invW20 == 0 || k.n_apple4 > 32 * 16) { delete hm; delete h; return SSD_ERR_INVALID; }
+
+    int stage_budget = 6144;
+    if (const char* s = getenv("SSD_B200_STAGE_BYTES")) stage_budget = atoi(s);
+    k.chunk = stage_budget / k.AS; if (k.chunk < 1) k.chunk = 1; if (k.chunk > n) k.chunk = n;
+    k.off_ovl = k.GS; k.off_pmap = 2 * k.GS; k.off_stage = k.off_pmap + k.PMS;
+    k.smem_per_warp = k.off_stage + k.chunk * k.AS;
+    h->smem_bytes = (size_t)kWarps * k.smem_per_warp;
+    h->device = cfg->device;
+
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_map, sizeof(MapDev));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_map, hm, sizeof(MapDev), cudaMemcpyHostToDevice);
+    delete hm;
+    if (e != cudaSuccess) {
+        if (h->d_map) cudaFree(h->d_map);
+        delete h;
+        return cuda_fail(e);
+    }
+    k.map = h->d_map;
+    *out = h;
+    return SSD_OK;
+}
+
+int ssd_destroy(ssd_handle* h) {
+    if (!h) return SSD_ERR_INVALID;
+    cudaFree(h->d_map);
+    delete h;
+    return SSD_OK;
+}
+
+int ssd_get_layout(const ssd_handle* h, ssd_layout* o) {
+    if (!h || !o) return SSD_ERR_INVALID;
+    const KParams& k = h->kp;
+    o->n_actions = k.n_actions; o->n_cells = k.G; o->obs_n = k.N; o->grid_stride = k.GS; o->agent_stride = k.NA;
+    o->obs_plane_stride = k.PS; o->obs_agent_stride = k.AS; o->obs_env_stride = k.ES;
+    o->n_apple_pts = k.n_apple; o->n_waste_pts = k.n_waste; o->n_spawn_pts = k.n_spawn; o->reserved = 0;
+    return SSD_OK;
+}
+
+int ssd_reset(ssd_handle* h, const ssd_state* st, const uint8_t* mask, const ssd_draws* draws, uint8_t* obs, void* stream) {
+    KParams k;
+    const int rc = fill_common(h, st, draws, k);
+    if (rc) return rc;
+    k.mask = mask; k.obs = obs;
+    return launch<MODE_RESET>(h, k, stream);
+}
+
+int ssd_step(ssd_handle* h, const ssd_state* st, const uint8_t* actions, const ssd_draws* draws,
+             const ssd_step_out* out, void* stream) {
+    KParams k;
+    const int rc = fill_common(h, st, draws, k);
+    if (rc) return rc;
+    if (!actions || !out || !out->reward || !out->clean || !out->apple_cnt || !out->done) return SSD_ERR_INVALID;
+    k.actions = actions; k.reward = out->reward; k.clean = out->clean; k.apple_cnt = out->apple_cnt; k.done = out->done;
+    k.obs = out->obs; k.state_rgb = out->state_rgb;
+    return launch<MODE_STEP>(h, k, stream);
+}
+
+int ssd_render(ssd_handle* h, const ssd_state* st, uint8_t* obs, uint8_t* state_rgb, void* stream) {
+    KParams k;
+    const int rc = fill_common(h, st, nullptr, k);
+    if (rc) return rc;
+    if (!obs && !state_rgb) return SSD_ERR_INVALID;
+    k.obs = obs; k.state_rgb = state_rgb;
+    return launch<MODE_RENDER>(h, k, stream);
+}
+
+int ssd_step_host(ssd_handle* h, const ssd_state* st, const uint8_t* h_actions, uint8_t* d_actions,
+                  const ssd_step_out* d_out, const ssd_step_out* h_out, void* stream) {
+    if (!h || !h_actions || !d_actions || !d_out || !h_out) return SSD_ERR_INVALID;
+    const KParams& k = h->kp;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = (size_t)k.B;
+    SSD_CUDA(cudaMemcpyAsync(d_actions, h_actions, B * k.n, cudaMemcpyHostToDevice, s));
+    const int rc = ssd_step(h, st, d_actions, nullptr, d_out, stream);
+    if (rc) return rc;
+    if (h_out->reward) SSD_CUDA(cudaMemcpyAsync(h_out->reward, d_out->reward, B * k.n, cudaMemcpyDeviceToHost, s));
+    if (h_out->clean) SSD_CUDA(cudaMemcpyAsync(h_out->clean, d_out->clean, B * k.n, cudaMemcpyDeviceToHost, s));
+    if (h_out->apple_cnt) SSD_CUDA(cudaMemcpyAsync(h_out->apple_cnt, d_out->apple_cnt, B * 2, cudaMemcpyDeviceToHost, s));
+    if (h_out->done) SSD_CUDA(cudaMemcpyAsync(h_out->done, d_out->done, B, cudaMemcpyDeviceToHost, s));
+    if (h_out->obs && d_out->obs) SSD_CUDA(cudaMemcpyAsync(h_out->obs, d_out->obs, B * k.ES, cudaMemcpyDeviceToHost, s));
+    if (h_out->state_rgb && d_out->state_rgb)
+        SSD_CUDA(cudaMemcpyAsync(h_out->state_rgb, d_out->state_rgb, B * 3 * k.G, cudaMemcpyDeviceToHost, s));
+    SSD_CUDA(cudaStreamSynchronize(s));
+    return SSD_OK;
+}
+
+int ssd_incentive(const int64_t* actions_inc, const float* reward, int64_t rows, int32_t n_agents,
+                  float incentive, float cost, float ratio, int32_t max_seq_length,
+                  float* rewards_for_env, float* rewards_for_inc, float* recv_sign, void* stream) {
+    if (!actions_inc || !reward || !rewards_for_env || !rewards_for_inc || rows < 0 || n_agents < 1 || max_seq_length == 0)
+        return SSD_ERR_INVALID;
+    if (rows == 0) return SSD_OK;
+    // max_seq_length > 0: true division (torch CPU); < 0: multiply by 1/|T| (torch CUDA scalar-divisor path)
+    const int recip = max_seq_length < 0;
+    const float T = (float)abs(max_seq_length);
+    const long long total = (long long)rows * n_agents;
+    const int threads = 256;
+    incentive_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long*>(actions_inc), reward, rows, n_agents, incentive, cost, ratio, T, recip,
+        rewards_for_env, rewards_for_inc, recv_sign);
+    SSD_CUDA(cudaGetLastError());
+    return SSD_OK;
+}
+
+int64_t ssd_launch_count(const ssd_handle* h) { return h ? h->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+"""PyMARL ``MultiAgentEnv`` facade over the CUDA simulator (one env instance).
+
+Drop-in for ``envs.REGISTRY['cleanup' | 'harvest']`` of the reference
+(src/envs/__init__.py:6-11): same constructor kwargs (config/envs/*.yaml
+``env_args``), same method names, argument meaning, return types and error
+behaviour as ``MapEnv`` (src/envs/ssd/map_env.py:874-1022), so the unchanged
+``EpisodeRunner`` (src/runners/episode_runner.py) and ``run_sequential`` drive it.
+
+Every transition / observation comes from the sm_100a kernels; this file only
+converts device buffers to the exact Python / NumPy types the callers expect.
+"""
+from __future__ import annotations
+
+import os
+from functools import partial
+
+import numpy as np
+import torch
+
+from . import mapspec
+from .batch_env import SSDBatchEnv
+
+
+class MultiAgentEnv(object):
+    """Abstract surface (mirrors src/envs/multiagentenv.py:6-75)."""
+
+    def step(self, actions):
+        raise NotImplementedError
+
+    def get_obs(self):
+        raise NotImplementedError
+
+    def get_own_feature_size(self):
+        return None
+
+    def get_obs_agent(self, agent_id):
+        raise NotImplementedError
+
+    def get_obs_size(self):
+        raise NotImplementedError
+
+    def get_state(self):
+        raise NotImplementedError
+
+    def get_state_size(self):
+        raise NotImplementedError
+
+    def get_avail_actions(self):
+        raise NotImplementedError
+
+    def get_avail_agent_actions(self, agent_id):
+        raise NotImplementedError
+
+    def get_total_actions(self):
+        raise NotImplementedError
+
+    def reset(self):
+        raise NotImplementedError
+
+    def render(self):
+        raise NotImplementedError
+
+    def close(self):
+        raise NotImplementedError
+
+    def seed(self):
+        raise NotImplementedError
+
+    def save_replay(self):
+        raise NotImplementedError
+
+    def get_units_type_id(self):
+        return None
+
+    def get_env_info(self):
+        return {"state_shape": self.get_state_size(), "obs_shape": self.get_obs_size(),
+                "n_actions": self.get_total_actions(), "n_agents": self.n_agents,
+                "episode_limit": self.episode_limit, "units_type_id": self.get_units_type_id(),
+                "own_feature_size": self.get_own_feature_size()}
+
+
+class _SSDEnv(MultiAgentEnv):
+    ENV_NAME = None
+
+    def __init__(self, ascii_map=None, num_agents=1, render=False, seed=None, episode_limit=100,
+                 is_replay=False, view_size=7, map="default", extra_args=None, device=None, quiet=False):
+        extra = dict(random_spawn_point=False, random_spawn_rotation=0, disable_rotation_action=True,
+                     disable_fire_action=True, obs_color="simplified")
+        extra.update(extra_args or {})
+        device = device or os.environ.get("SSD_B200_DEVICE", "cuda:0")
+        self.sim = SSDBatchEnv(self.ENV_NAME, 1, num_agents, map=map, view_size=view_size,
+                               episode_limit=episode_limit, extra_args=extra, seed=0 if seed is None else int(seed),
+                               device=device, rows=ascii_map, want_state=True)
+        if not quiet:                                   # cleanup.py:56-58 / harvest.py:24-26
+            print("map difficulty: {}".format(map))
+            for row in self.sim.spec.rows:
+                print(row)
+        self.extra_args = extra
+        self.num_agents = self.n_agents = num_agents
+        self.n_actions = self.sim.n_actions
+        self.episode_limit = episode_limit
+        self.view_size = view_size
+        self.is_replay = is_replay
+        self.env_name = self.ENV_NAME
+        self._episode_steps = 0
+        self.rewards = None
+        self.clean_num = np.zeros(num_agents)
+        self.apple_den = np.zeros(num_agents)
+        self._actions_dev = torch.zeros((1, num_agents), dtype=torch.uint8, device=self.sim.device)
+        self.sim.reset()                                # valid state before the first reset()
+
+    # ------------------------------------------------------------------ step / reset
+    def step(self, actions):
+        """Returns reward, terminated, info (map_env.py:874-915)."""
+        acts = [int(a) for a in actions]
+        for a in acts[:self.num_agents]:
+            if not 0 <= a < self.n_actions:
+                raise KeyError(a)                        # agent.py:176,237 action_map lookup
+        self._actions_dev.copy_(torch.tensor([acts[:self.num_agents]], dtype=torch.uint8), non_blocking=False)
+        self.sim.step(self._actions_dev)
+        sim = self.sim
+        reward = sim.reward[0].cpu().numpy().astype(float)
+        if self.rewards is None:
+            self.rewards = reward
+        else:
+            self.rewards += reward
+        self._episode_steps += 1
+        terminated = bool(sim.done[0].item())            # python bool: SURVEY 8b pitfall
+        info = {}
+        if terminated:
+            collective_return = self.rewards.sum()
+            equality_metric = 1.0
+            if self.rewards.sum() != 0:
+                equality_metric = 1 - (np.abs(self.rewards.reshape(1, -1) - self.rewards.reshape(-1, 1)).sum()) / (
+                    2 * len(self.rewards) * np.abs(self.rewards).sum())
+            info = {"collective_return": collective_return, "equality_metric": equality_metric}
+        self.clean_num = sim.clean[0].cpu().numpy().astype(float)
+        density = int(sim.apple_cnt[0].item()) / sim.G
+        self.apple_den = np.full(self.n_agents, density, dtype=float)
+        info["clean_num"] = self.clean_num
+        info["apple_den"] = self.apple_den
+        return reward, terminated, info
+
+    def reset(self):
+        """Reset the environment (map_env.py:986-993); returns None like the reference."""
+        self.sim.reset()
+        self._episode_steps = 0
+        self.rewards = None
+        return
+
+    # ------------------------------------------------------------------ queries
+    def get_agent_pos(self):
+        return self.sim.agent_pos[0].cpu().numpy().astype(float)
+
+    def get_agent_orientation(self):
+        return mapspec.ORIENT_VEC[self.sim.agent_orient[0].cpu().numpy()].astype(float)
+
+    def _obs_u8(self):
+        return self.sim.obs_view()[0].cpu().numpy()
+
+    def get_obs(self):
+        """List of n arrays (3, N, N) float = u8 / 256 (map_env.py:923-945)."""
+        return list(self._obs_u8() / 256)
+
+    def get_obs_agent(self, agent_id):
+        return self._obs_u8()[int(agent_id)] / 256
+
+    def get_obs_size(self):
+        return (3, self.sim.N, self.sim.N)
+
+    def get_state(self):
+        """(3, H, W) float = u8 / 256 (map_env.py:950-957)."""
+        self.sim.render(want_obs=False, want_state=True)
+        return self.sim.state_rgb[0].cpu().numpy() / 256
+
+    def get_state_size(self):
+        return (3, self.sim.H, self.sim.W)
+
+    def get_own_feature_size(self):
+        return None
+
+    def get_avail_actions(self):
+        return [self.get_avail_agent_actions(i) for i in range(self.num_agents)]
+
+    def get_avail_agent_actions(self, agent_id):
+        available_actions = [1] * self.n_actions            # map_env.py:972-980 (advisory)
+        if self.extra_args["disable_rotation_action"]:
+            available_actions[5] = 0
+            available_actions[6] = 0
+        if self.extra_args["disable_fire_action"]:
+            available_actions[7] = 0
+        return available_actions
+
+    def get_total_actions(self):
+        return self.n_actions
+
+    def get_env_info(self):
+        info = super().get_env_info()
+        info["state_dims"] = (self.sim.H, self.sim.W)
+        info["obs_dims"] = (self.sim.N, self.sim.N)
+        return info
+
+    def get_stats(self):
+        return {}
+
+    def render(self):
+        return None
+
+    def close(self):
+        self.sim.close()
+
+    def seed(self):
+        return None
+
+    def save_replay(self):
+        return None
+
+
+class CleanupEnv(_SSDEnv):
+    ENV_NAME = "cleanup"
+
+
+class HarvestEnv(_SSDEnv):
+    ENV_NAME = "harvest"
+
+
+def env_fn(env, **kwargs) -> MultiAgentEnv:
+    return env(**kwargs)
+
+
+REGISTRY = {"harvest": partial(env_fn, env=HarvestEnv), "cleanup": partial(env_fn, env=CleanupEnv)}

@@ -168,3 +168,55 @@ def assert_traces_equal(a, b, what=""):
             bad = np.argwhere(x != y)
             raise AssertionError(f"{what}: first mismatch in '{k}' at index {bad[0].tolist()} "
                                  f"({x[tuple(bad[0])]} vs {y[tuple(bad[0])]}); {len(bad)} differing elements")
+
+
+class CudaBackend:
+    """One env instance on the GPU behind the lockstep surface (calls go through the C ABI)."""
+
+    def __init__(self, key, random_spawn=False, episode_limit=1000, device="cuda:0", **kw):
+        import torch
+        from homophily_marl_b200.batch_env import SSDBatchEnv
+        name, map_name, n, view, color = CONFIGS[key]
+        extra = dict(obs_color=color)
+        if random_spawn:
+            extra.update(random_spawn_point=True, random_spawn_rotation=None)
+        self.torch = torch
+        self.env = SSDBatchEnv(name, 1, n, map=map_name, view_size=view, episode_limit=episode_limit,
+                               extra_args=extra, device=device, want_state=True, **kw)
+
+    def reset(self, draws):
+        e = self.env
+        e.reset(draws=dict(spawn_key=draws["spawn_key"].reshape(1, e.n, e.G), rot=draws["rot"].reshape(1, e.n)))
+
+    def set_state(self, pos, orient, grid):
+        self.env.set_state(0, grid=grid, pos_rc=pos, orient=orient)
+
+    def step(self, actions, draws):
+        e, torch = self.env, self.torch
+        a = torch.as_tensor(np.asarray(actions, dtype=np.uint8).reshape(1, e.n), device=e.device)
+        e.step(a, draws={k: v.reshape(1, -1) for k, v in draws.items()}, want_state=True)
+        return (e.reward[0].cpu().numpy(), e.clean[0].cpu().numpy(),
+                int(e.apple_cnt[0].cpu().numpy().view(np.uint16)), bool(e.done[0].item()))
+
+    def snapshot(self):
+        e = self.env
+        e.render(want_obs=True, want_state=True)
+        return dict(grid=e.grid[0].cpu().numpy(), pos=e.agent_pos[0].cpu().numpy().astype(np.int32),
+                    orient=e.agent_orient[0].cpu().numpy(), obs=e.obs_view()[0].cpu().numpy(),
+                    state=e.state_rgb[0].cpu().numpy())
+
+
+def cluster_states(rs, spec, B):
+    """[B,n,2] positions clustered around random free cells (+ some duplicates) and [B,n] orientations."""
+    wall = np.asarray(spec.wall).reshape(spec.H, spec.W).astype(bool)
+    free = np.argwhere(~wall)
+    n = spec.n_agents
+    pos = np.zeros((B, n, 2), dtype=np.int32)
+    for b in range(B):
+        centre = free[rs.randint(len(free))]
+        d = np.abs(free - centre).sum(axis=1) + rs.rand(len(free)) * 0.5
+        near = free[np.argsort(d)[:n]]
+        pos[b] = near[rs.permutation(n)]
+        if n >= 2 and rs.rand() < 0.2:
+            pos[b, rs.randint(1, n)] = pos[b, 0]
+    return pos, rs.randint(0, 4, size=(B, n)).astype(np.uint8)
