@@ -33,7 +33,7 @@ class SsdConfig(C.Structure):
 class SsdLayout(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n_actions", "n_cells", "obs_n", "grid_stride", "agent_stride",
                                           "obs_plane_stride", "obs_agent_stride", "obs_env_stride",
-                                          "n_apple_pts", "n_waste_pts", "n_spawn_pts", "reserved")]
+                                          "n_apple_pts", "n_waste_pts", "n_spawn_pts", "obs_row_stride")]
 
 
 class SsdState(C.Structure):

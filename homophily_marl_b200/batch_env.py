@@ -104,7 +104,7 @@ class SSDBatchEnv:
         buf = self.obs_buf if buf is None else buf
         lay = self.layout
         return buf.as_strided((self.B, self.n, 3, self.N, self.N),
-                              (lay.obs_env_stride, lay.obs_agent_stride, lay.obs_plane_stride, self.N, 1))
+                              (lay.obs_env_stride, lay.obs_agent_stride, lay.obs_plane_stride, lay.obs_row_stride, 1))
 
     @property
     def grid(self):

@@ -6,12 +6,13 @@
 //     keeping the reference's sequential phase structure (map_env.py:477-661);
 //   * lanes are spawn candidates during apple/waste spawning (4 apple points or 2 waste
 //     points per Philox4x32-10 call);
-//   * lanes are pixel quads during the egocentric render: 4 pixels -> one 32-bit store per
-//     colour plane into a shared-memory staging tile that leaves the SM as ONE bulk
-//     asynchronous copy (cp.async.bulk shared->global, SASS UBLKCP) per agent chunk.
-// The env's grid is staged in shared memory for the whole step (compact copy for the logic,
-// zero-padded copy with agents overlaid for the render).  No tensor cores: nothing here is a
-// contraction.  HBM traffic per env-step is the algorithmic 2G + n(3N^2+11)+3 bytes (+ padding).
+//   * lanes are output pixel ROWS during the egocentric render: a row of the rotated window is one
+//     contiguous run in a zero-padded (or transposed) index map held in shared memory, so a lane
+//     realigns it with PRMT, colours 4 pixels per PRMT through an 8-entry register LUT and writes the
+//     finished row with one 256-bit (st.global.v8.b32, SASS STG.E.ENL2.256) or 128-bit store per plane.
+// The env's grid is staged in shared memory for the whole step.  No tensor cores: nothing here is a
+// contraction.  HBM traffic per env-step is the algorithmic 2G + n(3N^2+11)+3 bytes (+ row padding),
+// ~98% of it observation WRITES.
 //
 // Reference citations are relative to drdh/Homophily-MARL.
 #include <cuda_runtime.h>
@@ -22,10 +23,6 @@
 #include <new>
 
 #include "ssd_b200.h"
-
-#ifndef SSD_USE_BULK_STORE
-#define SSD_USE_BULK_STORE 1
-#endif
 
 namespace {
 
@@ -47,15 +44,18 @@ struct MapDev {
 
 struct KParams {
     int kind, B, n, H, W, G, V, N, NN;
-    int GS, NA, PS, AS, ES, PW, PH, PMS;      // strides (ssd_layout) + padded-map geometry
+    int GS, NA, RP, PS, AS, ES;               // strides (ssd_layout)
+    int PWp, PHp, off_M, off_MT, PMS;         // padded index maps M / MT: pitches, byte offsets, total bytes
+    int agents_uniform;                       // all agent colours equal -> no per-agent repaint
     int episode_limit, fire_cost, hit_penalty, beam_len, n_actions;
     int n_apple, n_waste, n_spawn, n_apple4, n_waste2;
     int random_spawn, spawn_rot;
-    int chunk, smem_per_warp, off_ovl, off_pmap, off_stage;
-    uint32_t invN20, invW20;                  // floor(x / N) == (x * invN20) >> 20 on the used ranges
+    int smem_per_warp, off_pmap;
+    uint32_t invN20, invW20, invMW20, invMTW20;   // floor(x / d) == (x * inv) >> 20 on the used ranges
     uint32_t seed_lo, seed_hi, gid_base;
     uint32_t thr_harvest[4];
     uint32_t lut[16];
+    uint32_t lut8[6];                         // 8-entry colour LUT per plane (lo, hi words): R, G, B
     const MapDev* map;
     uint8_t* grid; uint32_t* agent; int32_t* ep_ret; int32_t* t; uint32_t* tick;
     const uint8_t* actions; const uint8_t* mask;
@@ -183,8 +183,12 @@ __device__ __forceinline__ void update_moves(const KParams& p, const uint8_t* __
     }
 }
 
+// Agent occupancy is kept IN the staged grid: bit 7 of a cell byte is set while an agent stands on it
+// (the dict `agent_by_pos` / `[r, c] in self.agent_pos` tests of the reference become one bit test).
+constexpr uint8_t kOcc = 0x80;
+
 // ------------------------------------------------------------------ beams (map_env.py:663-769)
-__device__ __forceinline__ void beams(const KParams& p, uint8_t* sg, const uint8_t* ovl, int lane, bool is_agent,
+__device__ __forceinline__ void beams(const KParams& p, uint8_t* sg, int lane, bool is_agent,
                                       int act, int pos, int ori, int& reward, int& clean_num) {
     const bool fire = is_agent && act == 7;
     const bool clean = is_agent && act == 8 && p.kind == SSD_KIND_CLEANUP;
@@ -203,11 +207,10 @@ __device__ __forceinline__ void beams(const KParams& p, uint8_t* sg, const uint8
         if (lane < 3) {                                       // the three parallel rays (728-730)
             int q = posi + (lane == 0 ? d : (lane == 1 ? rs : -rs));
             for (int k = 0; k < p.beam_len; ++k) {            // maps are wall-enclosed: a ray cannot leave the map
-                const int code = sg[q];
+                const int v = sg[q], code = v & 0x7f;
                 if (code == SSD_CELL_WALL) break;             // 737
-                const int o = ovl[q];
-                if (o) {                                      // agents absorb beams (741-749)
-                    if (!is_clean) hit = o - 1;
+                if (v & kOcc) {                               // agents absorb beams (741-749)
+                    if (!is_clean) hit = q;
                     if (is_clean && code == SSD_CELL_WASTE) upd = q;
                     break;
                 }
@@ -216,26 +219,29 @@ __device__ __forceinline__ void beams(const KParams& p, uint8_t* sg, const uint8
             }
         }
         __syncwarp();
-        if (upd >= 0) sg[upd] = SSD_CELL_RIVER;
+        if (upd >= 0) sg[upd] = (uint8_t)(SSD_CELL_RIVER | (sg[upd] & kOcc));
         __syncwarp();
         const unsigned um = __ballot_sync(kFull, upd >= 0);
         if (lane == i && is_clean) clean_num = __popc(um);    // 672-673
-        if (p.hit_penalty != 0) {
+        if (p.hit_penalty != 0) {                             // hit(): the LAST index standing on the cell (agent.py:184-186)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) if (__shfl_sync(kFull, hit, s) == lane) reward -= p.hit_penalty;   // agent.py:184-186
+            for (int s = 0; s < 3; ++s) {
+                const int hq = __shfl_sync(kFull, hit, s);
+                const unsigned on = __ballot_sync(kFull, hq >= 0 && pos == hq);
+                if (on && lane == 31 - __clz(on)) reward -= p.hit_penalty;
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------ spawning (cleanup.py:165-204, harvest.py:92-122)
-__device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, const uint8_t* ovl, int lane, int env,
-                                      uint32_t gid, uint32_t tick) {
+__device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick) {
     const MapDev* __restrict__ m = p.map;
     uint32_t tA = 1, tW = 0;
     if (p.kind == SSD_KIND_CLEANUP) {
         int h = 0;                                            // compute_permitted_area: count 'H'
         for (int i = lane; i < (p.GS >> 2); i += 32)
-            h += __popc(__vcmpeq4(reinterpret_cast<const uint32_t*>(sg)[i], 0x03030303u)) >> 3;
+            h += __popc(__vcmpeq4(reinterpret_cast<const uint32_t*>(sg)[i] & 0x7f7f7f7fu, 0x03030303u)) >> 3;
         h = __reduce_add_sync(kFull, h);
         tA = __ldg(&m->thr_apple[h]);
         tW = __ldg(&m->thr_waste[h]);
@@ -253,7 +259,8 @@ __device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, const uint8
             for (int q = 0; q < 4; ++q) {
                 const int c = c4[q];
                 if (c == kNoPoint) continue;
-                if (ovl[c] != 0 || sg[c] == SSD_CELL_APPLE) continue;          // cleanup.py:171, harvest.py:105
+                const int v = sg[c];
+                if ((v & kOcc) || v == SSD_CELL_APPLE) continue;               // cleanup.py:171, harvest.py:105
                 uint32_t thr = tA;
                 if (p.kind == SSD_KIND_HARVEST) {
                     int cnt = 0;                                               // j^2+k^2 <= 2: the 3x3 block (harvest.py:107-116)
@@ -279,7 +286,7 @@ __device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, const uint8
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const uint32_t c = q ? pts.y : pts.x;
-                if (c == kNoPoint || sg[c] == SSD_CELL_WASTE) continue;        // cleanup.py:182
+                if (c == kNoPoint || (sg[c] & 0x7f) == SSD_CELL_WASTE) continue;   // cleanup.py:182
                 const uint32_t u = p.d_uwaste ? p.d_uwaste[(size_t)env * p.G + c] : (q ? r.z : r.x);
                 const uint32_t key = p.d_uwaste ? p.d_wkey[(size_t)env * p.G + c] : (q ? r.w : r.y);
                 if (u < tW && (key < bk || (key == bk && c < bc))) { bk = key; bc = c; }
@@ -301,102 +308,166 @@ __device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, const uint8
             for (int q = 0; q < 4; ++q) if ((decided >> (it * 4 + q)) & 1ull) sg[c4[q]] = SSD_CELL_APPLE;
         }
     }
-    if (wcell >= 0 && lane == 0) sg[wcell] = SSD_CELL_WASTE;
+    if (wcell >= 0 && lane == 0) sg[wcell] = (uint8_t)(SSD_CELL_WASTE | (sg[wcell] & kOcc));
     __syncwarp();
 }
 
 // ------------------------------------------------------------------ render (map_env.py:360-379, 418-446, 795-815, 923-957)
-__device__ __forceinline__ void bulk_store_wait_read() {
-#if SSD_USE_BULK_STORE
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#endif
+__device__ __forceinline__ void st_row32(uint8_t* dst, const uint32_t* w) {     // one full 32-byte sector per lane
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
-__device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint8_t* pmap, uint8_t* stage,
-                                       const uint32_t* lut_s, int lane, bool is_agent, int pos, int ori, int env) {
-    // zero-padded copy of the map in colour indices, agents overlaid (utility_funcs.py:58-116 without np.pad)
-    for (int i = lane; i < (p.PMS >> 4); i += 32)
-        reinterpret_cast<uint4*>(pmap)[i] = make_uint4(0x06060606u, 0x06060606u, 0x06060606u, 0x06060606u);
-    __syncwarp();
-    for (int c = lane; c < p.G; c += 32) {
-        const int r = (int)(((uint32_t)c * p.invW20) >> 20);
-        pmap[(r + p.V) * p.PW + (c - r * p.W) + p.V] = sg[c];
+// Row gather.  Two zero-padded copies of the map are kept in shared memory as colour INDICES:
+//   M  [padded row][padded col]  (pitch PWp)  and  MT [padded col][padded row]  (pitch PHp),
+// so that for every orientation an output row of the rotated egocentric window (np.rot90 k=1,3,0,2 for
+// LEFT, RIGHT, UP, DOWN; map_env.py:806-813) is ONE contiguous run of N bytes, ascending or descending:
+//   UP    out[y][:] = M [pr-V+y][pc-V ...]   ascending      DOWN  out[y][:] = M [pr+V-y][pc+V ...]  descending
+//   LEFT  out[y][:] = MT[pc+V-y][pr-V ...]   ascending      RIGHT out[y][:] = MT[pc-V+y][pr+V ...]  descending
+// A lane owns one (agent, y) output row: WR+1 aligned 32-bit loads, one PRMT per word to realign/reverse,
+// then the 8-entry colour LUT is applied to 4 pixels at a time with PRMT (selector = 4 index nibbles),
+// one PRMT per colour plane, and the finished row leaves the SM as one 32-byte (or 16-byte) global store
+// per plane.  Indices: 0-5 cell codes, 6 outside the map, 7 agent.
+template <int WR_T>
+__device__ __forceinline__ void gather_rows(const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane, uint32_t apack) {
+    const int WR = WR_T > 0 ? WR_T : (p.RP >> 2);
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(pmap);
+    const uint32_t lastmask = 0xffffffffu >> (8 * (4 * WR - p.N));
+    const uint32_t tr0 = p.lut8[0], tr1 = p.lut8[1], tg0 = p.lut8[2], tg1 = p.lut8[3], tb0 = p.lut8[4], tb1 = p.lut8[5];
+    const int units = p.n * p.N, iters = (units + 31) >> 5;
+    for (int it = 0; it < iters; ++it) {
+        const int u = it * 32 + lane;
+        const bool valid = u < units;
+        const int al = valid ? (int)(((uint32_t)u * p.invN20) >> 20) : 0;
+        const int y = u - al * p.N;
+        const uint32_t ap = __shfl_sync(kFull, apack, al);
+        if (!valid) continue;
+        const int pr = ap & 1023, pc = (ap >> 10) & 1023, o = ap >> 20;
+        const bool isMT = o < 2, desc = o & 1;
+        const int pitch = isMT ? p.PHp : p.PWp;
+        const int major = isMT ? pc : pr, minor = isMT ? pr : pc;
+        const int rowoff = (desc != isMT) ? p.V - y : y - p.V;
+        const int s0 = (isMT ? p.off_MT : p.off_M) + (major + rowoff) * pitch + minor + (desc ? p.V : -p.V);
+        const int sh = s0 & 3, ds = desc ? -1 : 1;
+        // PRMT selectors that realign (ascending) or realign + reverse (descending) a 4-byte window
+        const uint32_t sel = desc ? (uint32_t)((0x0123701267015670ull >> (16 * sh)) & 0xffffu) : (0x3210u + 0x1111u * sh);
+        int wi = s0 >> 2;
+        uint32_t prev = mw[wi];
+        uint8_t* dst = gobs + al * p.AS + y * p.RP;
+        uint32_t R[WR_T > 0 ? WR_T : 1], Gc[WR_T > 0 ? WR_T : 1], Bl[WR_T > 0 ? WR_T : 1];
+#pragma unroll
+        for (int k = 0; k < WR; ++k) {
+            wi += ds;
+            const uint32_t cur = mw[wi];
+            const uint32_t x = __byte_perm(prev, cur, sel);        // 4 colour indices, one per byte
+            prev = cur;
+            const uint32_t t = x | (x >> 4);
+            const uint32_t s16 = __byte_perm(t, 0u, 0x4420);       // -> 4 nibbles = PRMT selector
+            uint32_t r = __byte_perm(tr0, tr1, s16), g = __byte_perm(tg0, tg1, s16), b = __byte_perm(tb0, tb1, s16);
+            if (k == WR - 1) { r &= lastmask; g &= lastmask; b &= lastmask; }
+            if (WR_T > 0) { R[k] = r; Gc[k] = g; Bl[k] = b; }
+            else {
+                *reinterpret_cast<uint32_t*>(dst + 4 * k) = r;
+                *reinterpret_cast<uint32_t*>(dst + p.PS + 4 * k) = g;
+                *reinterpret_cast<uint32_t*>(dst + 2 * p.PS + 4 * k) = b;
+            }
+        }
+        if (WR_T == 8) { st_row32(dst, R); st_row32(dst + p.PS, Gc); st_row32(dst + 2 * p.PS, Bl); }
+        else if (WR_T == 4) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(R[0], R[1], R[2], R[3]);
+            *reinterpret_cast<uint4*>(dst + p.PS) = make_uint4(Gc[0], Gc[1], Gc[2], Gc[3]);
+            *reinterpret_cast<uint4*>(dst + 2 * p.PS) = make_uint4(Bl[0], Bl[1], Bl[2], Bl[3]);
+        }
     }
-    int ppos = 0;
-    if (is_agent) {
-        const int r = (int)(((uint32_t)pos * p.invW20) >> 20);
-        ppos = (r + p.V) * p.PW + (pos - r * p.W) + p.V;
-    }
-    __syncwarp();
-    const unsigned same = __match_any_sync(kFull, pos);
-    if (is_agent && lane == 31 - __clz(same)) pmap[ppos] = (uint8_t)agent_colour_index(lane);   // later index overwrites (370)
-    __syncwarp();
+}
 
-    if (p.state_rgb) {                                        // get_state: unrotated full map (950-957)
+// Builds one padded index map word by word: dest word j of padded row `row` holds source cells
+// base + (4j - V + k) * step, k = 0..3 (step 1: M from grid rows, step W: MT from grid columns).
+__device__ __forceinline__ void build_map(const KParams& p, const uint8_t* sg, uint8_t* map, int lane,
+                                          int rows, int len, int pitch, int row_stride, int step, uint32_t inv_nw20) {
+    const int w0 = p.V >> 2, nw = ((p.V + len - 1) >> 2) - w0 + 1;
+    const int total = rows * nw;
+    for (int i = lane; i < total; i += 32) {
+        const int row = (int)(((uint32_t)i * inv_nw20) >> 20), j = i - row * nw + w0;
+        const int e0 = 4 * j - p.V;                           // index along the row of the first byte of this word
+        const uint8_t* src = sg + row * row_stride + e0 * step;
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = e0 + k;
+            const uint32_t v = (e >= 0 && e < len) ? (uint32_t)src[k * step] : 6u;
+            w |= v << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(map + (row + p.V) * pitch + 4 * j) = w;
+    }
+}
+
+__device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
+                                       int lane, bool is_agent, int pos, int ori, int env) {
+    const unsigned same = __match_any_sync(kFull, pos);
+    const bool top = is_agent && lane == 31 - __clz(same);   // later index overwrites (map_env.py:370)
+    int r0 = 0, c0 = 0;
+    if (is_agent) { r0 = (int)(((uint32_t)pos * p.invW20) >> 20); c0 = pos - r0 * p.W; }
+
+    if (p.state_rgb) {                                        // get_state: unrotated full map (map_env.py:950-957)
         uint8_t* out = p.state_rgb + (size_t)env * 3 * p.G;
         for (int c = lane; c < p.G; c += 32) {
-            const int r = (int)(((uint32_t)c * p.invW20) >> 20);
-            const uint32_t rgb = lut_s[pmap[(r + p.V) * p.PW + (c - r * p.W) + p.V]];
+            const uint32_t rgb = lut_s[sg[c]];
             out[c] = (uint8_t)rgb; out[p.G + c] = (uint8_t)(rgb >> 8); out[2 * p.G + c] = (uint8_t)(rgb >> 16);
+        }
+        __syncwarp();                                         // orders the agent overlay after the cell colours
+        if (top) {
+            const uint32_t rgb = lut_s[agent_colour_index(lane)];
+            out[pos] = (uint8_t)rgb; out[p.G + pos] = (uint8_t)(rgb >> 8); out[2 * p.G + pos] = (uint8_t)(rgb >> 16);
         }
     }
     if (!p.obs) return;
 
-    const int quads = p.PS >> 2;
-    const int tail = p.AS - 3 * p.PS;                         // 0..12 pad bytes per agent block
-    for (int a0 = 0; a0 < p.n; a0 += p.chunk) {
-        const int ka = min(p.chunk, p.n - a0);
-        if (a0 > 0) { if (lane == 0) bulk_store_wait_read(); __syncwarp(); }   // staging tile is being re-used
-        for (int al = 0; al < ka; ++al) {
-            const int a = a0 + al;
-            const int base = __shfl_sync(kFull, ppos, a);
-            const int o = __shfl_sync(kFull, ori, a);
-            // source = base + A*y + B*x + C   (np.rot90 k = 1, 3, 0, 2 for LEFT, RIGHT, UP, DOWN; 806-813)
-            int A, Bc, C;
-            if (o == 2)      { A = p.PW;  Bc = 1;     C = -p.V * p.PW - p.V; }
-            else if (o == 0) { A = -1;    Bc = p.PW;  C = -p.V * p.PW + p.V; }
-            else if (o == 3) { A = -p.PW; Bc = -1;    C = p.V * p.PW + p.V; }
-            else             { A = 1;     Bc = -p.PW; C = p.V * p.PW - p.V; }
-            const int wrap = A - p.N * Bc;
-            uint8_t* dst = stage + al * p.AS;
-            for (int q = lane; q < quads; q += 32) {
-                const int p0 = q << 2;
-                int y = (int)(((uint32_t)p0 * p.invN20) >> 20);
-                int x = p0 - y * p.N;
-                int src = base + C + A * y + Bc * x;
-                uint32_t px[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    px[k] = (p0 + k < p.NN) ? lut_s[pmap[src]] : 0u;
-                    src += Bc;
-                    if (++x == p.N) { x = 0; src += wrap; }
-                }
-                const uint32_t lo = __byte_perm(px[0], px[1], 0x5140), hi = __byte_perm(px[2], px[3], 0x5140);
-                const uint32_t lb = __byte_perm(px[0], px[1], 0x0062), hb = __byte_perm(px[2], px[3], 0x0062);
-                *reinterpret_cast<uint32_t*>(dst + p0) = __byte_perm(lo, hi, 0x5410);
-                *reinterpret_cast<uint32_t*>(dst + p.PS + p0) = __byte_perm(lo, hi, 0x7632);
-                *reinterpret_cast<uint32_t*>(dst + 2 * p.PS + p0) = __byte_perm(lb, hb, 0x5410);
-            }
-            if (lane < (tail >> 2)) *reinterpret_cast<uint32_t*>(dst + 3 * p.PS + 4 * lane) = 0u;
-        }
-        uint8_t* gdst = p.obs + (size_t)env * p.ES + (size_t)a0 * p.AS;
-        const int bytes = ka * p.AS;
-#if SSD_USE_BULK_STORE
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
-        __syncwarp();
-        if (lane == 0) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                         :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-#else
-        __syncwarp();
-        for (int i = lane; i < (bytes >> 4); i += 32)
-            reinterpret_cast<uint4*>(gdst)[i] = reinterpret_cast<const uint4*>(stage)[i];
-#endif
-    }
-    if (lane == 0) bulk_store_wait_read();                    // smem must outlive the async reads
+    // zero-padded index maps (utility_funcs.py:58-116 without np.pad)
+    for (int i = lane; i < (p.PMS >> 4); i += 32)
+        reinterpret_cast<uint4*>(pmap)[i] = make_uint4(0x06060606u, 0x06060606u, 0x06060606u, 0x06060606u);
+    const int pr = r0 + p.V, pc = c0 + p.V;
+    const uint32_t apack = (uint32_t)pr | ((uint32_t)pc << 10) | ((uint32_t)ori << 20);
+    const bool needM = __ballot_sync(kFull, is_agent && ori >= 2) != 0;
+    const bool needMT = __ballot_sync(kFull, is_agent && ori < 2) != 0;
     __syncwarp();
+    uint8_t* M = pmap + p.off_M;
+    uint8_t* MT = pmap + p.off_MT;
+    if (needM) build_map(p, sg, M, lane, p.H, p.W, p.PWp, p.W, 1, p.invMW20);
+    if (needMT) build_map(p, sg, MT, lane, p.W, p.H, p.PHp, 1, p.W, p.invMTW20);
+    __syncwarp();
+    if (top) { M[pr * p.PWp + pc] = 7; MT[pc * p.PHp + pr] = 7; }
+    __syncwarp();
+
+    uint8_t* gobs = p.obs + (size_t)env * p.ES;
+    if (p.RP == 32) gather_rows<8>(p, pmap, gobs, lane, apack);
+    else if (p.RP == 16) gather_rows<4>(p, pmap, gobs, lane, apack);
+    else gather_rows<0>(p, pmap, gobs, lane, apack);
+    const int tail = p.AS - 3 * p.PS;                         // pad bytes per agent block (0 for the shipped views)
+    if (tail) for (int i = lane; i < p.n * (tail >> 2); i += 32)
+        *reinterpret_cast<uint32_t*>(gobs + (i / (tail >> 2)) * p.AS + 3 * p.PS + 4 * (i % (tail >> 2))) = 0u;
+    if (!p.agents_uniform) {
+        // full-colour scheme: every visible agent is re-painted with its own colour (after the row stores)
+        __syncwarp();
+        const int pairs = p.n * p.n, iters = (pairs + 31) >> 5;
+        for (int it = 0; it < iters; ++it) {
+            const int q = it * 32 + lane;
+            const bool valid = q < pairs;
+            const int al = valid ? q / p.n : 0, j = valid ? q - al * p.n : 0;
+            const uint32_t api = __shfl_sync(kFull, apack, al), apj = __shfl_sync(kFull, apack, j);
+            const bool topj = __shfl_sync(kFull, (int)top, j);
+            if (!valid || !topj) continue;
+            const int a = (int)(apj & 1023) - (int)(api & 1023) + p.V, b = (int)((apj >> 10) & 1023) - (int)((api >> 10) & 1023) + p.V;
+            if (a < 0 || a >= p.N || b < 0 || b >= p.N) continue;
+            const int o = api >> 20;
+            int y, x;
+            if (o == 2) { y = a; x = b; } else if (o == 0) { x = a; y = p.N - 1 - b; }
+            else if (o == 3) { y = p.N - 1 - a; x = p.N - 1 - b; } else { x = p.N - 1 - a; y = b; }
+            const uint32_t rgb = lut_s[agent_colour_index(j)];
+            uint8_t* d = gobs + al * p.AS + y * p.RP + x;
+            d[0] = (uint8_t)rgb; d[p.PS] = (uint8_t)(rgb >> 8); d[2 * p.PS] = (uint8_t)(rgb >> 16);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -412,16 +483,13 @@ __global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant_
     if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
 
     uint8_t* sg = smem + (size_t)warp * p.smem_per_warp;
-    uint8_t* ovl = sg + p.off_ovl;
     uint8_t* pmap = sg + p.off_pmap;
-    uint8_t* stage = sg + p.off_stage;
     const bool is_agent = lane < p.n;
     const uint32_t gid = p.gid_base + (uint32_t)env;
     uint32_t tick = p.tick[env];
     int pos = -1 - lane, ori = 0, ep_ret = 0;
 
-    // zero the agent-occupancy tile, stage the grid
-    for (int i = lane; i < (p.GS >> 4); i += 32) reinterpret_cast<uint4*>(ovl)[i] = make_uint4(0, 0, 0, 0);
+    // stage the grid
     if (MODE == MODE_RESET) {
         for (int i = lane; i < (p.GS >> 4); i += 32)
             reinterpret_cast<uint4*>(sg)[i] = __ldg(reinterpret_cast<const uint4*>(p.map->base_grid) + i);
@@ -441,15 +509,17 @@ __global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant_
         const int act = is_agent ? (int)p.actions[(size_t)env * p.n + lane] : 255;
         int reward = 0, clean_num = 0;
         update_moves(p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
-        // consume in index order: the lowest index on a cell eats the apple (253-256)
+        // consume in index order: the lowest index on a cell eats the apple (253-256); mark occupancy
         const unsigned same = __match_any_sync(kFull, pos);
-        const bool eats = is_agent && sg[pos < 0 ? 0 : pos] == SSD_CELL_APPLE && lane == __ffs(same) - 1;
-        if (is_agent && lane == 31 - __clz(same)) ovl[pos] = (uint8_t)(lane + 1);           // dict: last index wins
+        const int here = is_agent ? sg[pos] : 0;
         __syncwarp();
-        if (eats) { reward += 1; sg[pos] = SSD_CELL_EMPTY; }
+        if (is_agent && lane == __ffs(same) - 1) {
+            if (here == SSD_CELL_APPLE) { reward += 1; sg[pos] = kOcc | SSD_CELL_EMPTY; }
+            else sg[pos] = (uint8_t)(kOcc | here);
+        }
         __syncwarp();
-        beams(p, sg, ovl, lane, is_agent, act, pos, ori, reward, clean_num);                // 259-260
-        spawn(p, sg, ovl, lane, env, gid, tick);                                            // 263
+        beams(p, sg, lane, is_agent, act, pos, ori, reward, clean_num);                     // 259-260
+        spawn(p, sg, lane, env, gid, tick);                                                 // 263
         // apple density numerator (291-292): after consume + spawn no apple lies under an agent
         int apples = 0;
         for (int i = lane; i < (p.GS >> 2); i += 32)
@@ -489,15 +559,17 @@ __global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant_
             if (p.spawn_rot >= 0) ori = p.spawn_rot;
             else ori = p.d_rot ? (int)(p.d_rot[(size_t)env * p.n + lane] & 3) : (int)(philox_word(p, gid, tick, 4u, (uint32_t)lane) >> 30);
         }
-        const unsigned same = __match_any_sync(kFull, pos);
-        if (is_agent && lane == 31 - __clz(same)) ovl[pos] = (uint8_t)(lane + 1);
+        if (is_agent) sg[pos] |= kOcc;                         // distinct spawn points: no two lanes share a cell
         __syncwarp();
-        spawn(p, sg, ovl, lane, env, gid, tick);                                            // custom_map_update (313)
+        spawn(p, sg, lane, env, gid, tick);                                                 // custom_map_update (313)
         ep_ret = 0;
         if (lane == 0) { p.t[env] = 0; p.tick[env] = tick + 1; }
     }
 
-    if (MODE != MODE_RENDER) {                                 // write the state back
+    if (MODE != MODE_RENDER) {                                 // strip the occupancy bits, write the state back
+        const unsigned same = __match_any_sync(kFull, pos);
+        if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
+        __syncwarp();
         uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * p.GS);
         for (int i = lane; i < (p.GS >> 4); i += 32) dst[i] = reinterpret_cast<const uint4*>(sg)[i];
         if (is_agent) {
@@ -506,7 +578,7 @@ __global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant_
             p.ep_ret[(size_t)env * p.NA + lane] = ep_ret;
         }
     }
-    if (p.obs || p.state_rgb) render(p, sg, pmap, stage, lut_s, lane, is_agent, pos, ori, env);
+    if (p.obs || p.state_rgb) render(p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
 }
 
 // ------------------------------------------------------------------ incentive bookkeeping (homophily_learner.py:98-115)
@@ -656,24 +728,38 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     KParams& k = h->kp;
     k.kind = cfg->kind; k.B = cfg->n_envs; k.n = n; k.H = H; k.W = W; k.G = G; k.V = V; k.N = 2 * V + 1; k.NN = k.N * k.N;
     k.GS = round_up(G, 16); k.NA = round_up(n, 4);
-    k.PS = round_up(k.NN, 4); k.AS = round_up(3 * k.PS, 16); k.ES = n * k.AS;
-    k.PW = W + 2 * V; k.PH = H + 2 * V; k.PMS = round_up(k.PW * k.PH, 16);
+    k.RP = round_up(k.N, 4); k.PS = k.N * k.RP; k.AS = round_up(3 * k.PS, 16); k.ES = n * k.AS;
+    // padded index maps; word pitch kept odd so that lanes gathering consecutive rows hit distinct banks
+    k.PWp = round_up(W + 2 * V, 4); if (((k.PWp >> 2) & 1) == 0) k.PWp += 4;
+    k.PHp = round_up(H + 2 * V, 4); if (((k.PHp >> 2) & 1) == 0) k.PHp += 4;
+    k.off_M = 16;
+    k.off_MT = k.off_M + round_up((H + 2 * V) * k.PWp, 16) + 16;
+    k.PMS = k.off_MT + round_up((W + 2 * V) * k.PHp, 16) + 16;
     k.episode_limit = cfg->episode_limit; k.fire_cost = cfg->fire_cost; k.hit_penalty = cfg->hit_penalty;
     k.beam_len = cfg->beam_len; k.n_actions = cfg->kind == SSD_KIND_CLEANUP ? 9 : 8;
     k.n_apple = na; k.n_waste = nw; k.n_spawn = ns; k.n_apple4 = (na + 3) / 4; k.n_waste2 = (nw + 1) / 2;
     k.random_spawn = cfg->random_spawn_point != 0; k.spawn_rot = cfg->spawn_rotation < 0 ? -1 : cfg->spawn_rotation;
-    k.invN20 = magic20(k.N, k.PS + 4); k.invW20 = magic20(W, G + 1);
+    k.invN20 = magic20(k.N, SSD_MAX_AGENTS * k.N + 64); k.invW20 = magic20(W, G + 1);
     k.seed_lo = (uint32_t)cfg->seed; k.seed_hi = (uint32_t)(cfg->seed >> 32); k.gid_base = cfg->env_gid_base;
     for (int i = 0; i < 4; ++i) k.thr_harvest[i] = cfg->thr_harvest[i];
     for (int i = 0; i < 16; ++i)
         k.lut[i] = (uint32_t)cfg->color_lut[i][0] | ((uint32_t)cfg->color_lut[i][1] << 8) | ((uint32_t)cfg->color_lut[i][2] << 16);
+    k.agents_uniform = 1;
+    for (int i = 8; i < 16; ++i) if (k.lut[i] != k.lut[7]) k.agents_uniform = 0;
+    for (int ch = 0; ch < 3; ++ch) {                          // 8-entry per-plane LUT: indices 0-6 + 7 = agent
+        uint32_t lo = 0, hi = 0;
+        for (int i = 0; i < 4; ++i) { lo |= (uint32_t)cfg->color_lut[i][ch] << (8 * i); hi |= (uint32_t)cfg->color_lut[4 + i][ch] << (8 * i); }
+        k.lut8[2 * ch] = lo; k.lut8[2 * ch + 1] = hi;
+    }
     if (k.invN20 == 0 || k.invW20 == 0 || k.n_apple4 > 32 * 16) { delete hm; delete h; return SSD_ERR_INVALID; }
 
-    int stage_budget = 6144;
-    if (const char* s = getenv("SSD_B200_STAGE_BYTES")) stage_budget = atoi(s);
-    k.chunk = stage_budget / k.AS; if (k.chunk < 1) k.chunk = 1; if (k.chunk > n) k.chunk = n;
-    k.off_ovl = k.GS; k.off_pmap = 2 * k.GS; k.off_stage = k.off_pmap + k.PMS;
-    k.smem_per_warp = k.off_stage + k.chunk * k.AS;
+    {
+        const int nwM = ((V + W - 1) >> 2) - (V >> 2) + 1, nwMT = ((V + H - 1) >> 2) - (V >> 2) + 1;
+        k.invMW20 = magic20(nwM, H * nwM + 32); k.invMTW20 = magic20(nwMT, W * nwMT + 32);
+        if (k.invMW20 == 0 || k.invMTW20 == 0) { delete hm; delete h; return SSD_ERR_INVALID; }
+    }
+    k.off_pmap = k.GS;
+    k.smem_per_warp = k.off_pmap + k.PMS;
     h->smem_bytes = (size_t)kWarps * k.smem_per_warp;
     h->device = cfg->device;
 
@@ -703,7 +789,7 @@ int ssd_get_layout(const ssd_handle* h, ssd_layout* o) {
     const KParams& k = h->kp;
     o->n_actions = k.n_actions; o->n_cells = k.G; o->obs_n = k.N; o->grid_stride = k.GS; o->agent_stride = k.NA;
     o->obs_plane_stride = k.PS; o->obs_agent_stride = k.AS; o->obs_env_stride = k.ES;
-    o->n_apple_pts = k.n_apple; o->n_waste_pts = k.n_waste; o->n_spawn_pts = k.n_spawn; o->reserved = 0;
+    o->n_apple_pts = k.n_apple; o->n_waste_pts = k.n_waste; o->n_spawn_pts = k.n_spawn; o->obs_row_stride = k.RP;
     return SSD_OK;
 }
 

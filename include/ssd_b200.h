@@ -83,11 +83,11 @@ typedef struct ssd_layout {
     int32_t obs_n;            /* N = 2V+1                                       */
     int32_t grid_stride;      /* bytes per env in `grid` (G rounded up to 16)   */
     int32_t agent_stride;     /* entries per env in `agent` / `ep_ret`          */
-    int32_t obs_plane_stride; /* bytes between colour planes  (N*N rounded to 4) */
+    int32_t obs_plane_stride; /* bytes between colour planes (= N * obs_row_stride)   */
     int32_t obs_agent_stride; /* bytes between agents (3 planes rounded to 16)  */
     int32_t obs_env_stride;   /* bytes between envs = n_agents * obs_agent_stride */
     int32_t n_apple_pts, n_waste_pts, n_spawn_pts;
-    int32_t reserved;
+    int32_t obs_row_stride;   /* bytes between pixel rows (N rounded up to 4); pad bytes are 0 */
 } ssd_layout;
 
 /* Persistent per-env state (MapEnv.world_map, Agent.pos/orientation, _episode_steps, rewards). */
@@ -105,7 +105,7 @@ typedef struct ssd_step_out {
     uint8_t*  clean;      /* [B][n]   info["clean_num"]                                 */
     uint16_t* apple_cnt;  /* [B]      info["apple_den"] * H*W                           */
     uint8_t*  done;       /* [B]      terminated                                        */
-    uint8_t*  obs;        /* [B][obs_env_stride] u8 RGB planes (get_obs * 256) or NULL  */
+    uint8_t*  obs;        /* [B][obs_env_stride] u8 RGB planes, rows padded to obs_row_stride (get_obs * 256) or NULL */
     uint8_t*  state_rgb;  /* [B][3][H][W] (get_state * 256) or NULL                     */
 } ssd_step_out;
 

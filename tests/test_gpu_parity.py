@@ -159,7 +159,7 @@ def test_step_host_equals_device_step():
         assert np.array_equal(io["apple_cnt"].numpy().view(np.uint16), out["apple_cnt"])
         lay = env.layout
         host_obs = io["obs"].as_strided((64, 5, 3, env.N, env.N),
-                                        (lay.obs_env_stride, lay.obs_agent_stride, lay.obs_plane_stride, env.N, 1))
+                                        (lay.obs_env_stride, lay.obs_agent_stride, lay.obs_plane_stride, lay.obs_row_stride, 1))
         assert np.array_equal(host_obs.numpy(), out["obs"])
 
 
@@ -195,8 +195,8 @@ def test_obs_padding_bytes_stay_zero_and_ring_buffers_work():
         assert np.array_equal(env.obs_view(buf).cpu().numpy(), out["obs"])
         lay = env.layout
         flat = buf.view(16, env.n, lay.obs_agent_stride).cpu().numpy()
-        planes = flat[:, :, : 3 * lay.obs_plane_stride].reshape(16, env.n, 3, lay.obs_plane_stride)
-        assert (planes[..., env.N * env.N:] == 0).all() and (flat[:, :, 3 * lay.obs_plane_stride:] == 0).all()
+        planes = flat[:, :, : 3 * lay.obs_plane_stride].reshape(16, env.n, 3, env.N, lay.obs_row_stride)
+        assert (planes[..., env.N:] == 0).all() and (flat[:, :, 3 * lay.obs_plane_stride:] == 0).all()
 
 
 def test_hit_penalty_and_fire_cost_parameters():
