@@ -45,7 +45,9 @@ struct MapDev {
 struct KParams {
     int kind, B, n, H, W, G, V, N, NN;
     int GS, NA, RP, PS, AS, ES;               // strides (ssd_layout)
-    int PWp, PHp, off_M, off_MT, PMS;         // padded index maps M / MT: pitches, byte offsets, total bytes
+    int pitchM, pitchT, off_map[4], PMS;      // nibble maps (index = orientation: MT, MTR, M, MR): row pitches, byte offsets, total bytes
+    int LPn, nw8M, nw8T;                      // left pad in nibbles (V rounded up to 8), words per map row holding cells
+    uint32_t maskM8, maskT8;                  // valid-nibble mask of the last word of a map row
     int agents_uniform;                       // all agent colours equal -> no per-agent repaint
     int episode_limit, fire_cost, hit_penalty, beam_len, n_actions;
     int n_apple, n_waste, n_spawn, n_apple4, n_waste2;
@@ -79,6 +81,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 }
 __device__ __forceinline__ uint32_t pick(const uint4& v, int i) {
     return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+// warp-strided loop with the first trip peeled (trip counts here are almost always 0 or 1)
+template <typename F>
+__device__ __forceinline__ void warp_for(int n, int lane, F f) {
+    int i = lane;
+    if (i < n) f(i);
+    for (i += 32; i < n; i += 32) f(i);
+}
+// bit 7 of every byte of w that differs from the corresponding byte of pat (exact, no cross-byte borrow)
+__device__ __forceinline__ uint32_t ne_bytes(uint32_t w, uint32_t pat) {
+    const uint32_t t = w ^ pat;
+    return (((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;
+}
+__device__ __forceinline__ int count_eq16(const uint4& v, uint32_t pat) {      // bytes of a 16-byte vector equal to pat's byte
+    const uint32_t m = (ne_bytes(v.x, pat) >> 7) | (ne_bytes(v.y, pat) >> 6) | (ne_bytes(v.z, pat) >> 5) | (ne_bytes(v.w, pat) >> 4);
+    return 16 - __popc(m);
 }
 // draw streams: 0 mover priority, 1 apple, 2 waste (u, order key), 3 spawn key, 4 spawn rotation
 __device__ __forceinline__ uint32_t philox_word(const KParams& p, uint32_t gid, uint32_t tick, uint32_t stream, uint32_t idx) {
@@ -239,9 +257,12 @@ __device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, int lane, i
     const MapDev* __restrict__ m = p.map;
     uint32_t tA = 1, tW = 0;
     if (p.kind == SSD_KIND_CLEANUP) {
-        int h = 0;                                            // compute_permitted_area: count 'H'
-        for (int i = lane; i < (p.GS >> 2); i += 32)
-            h += __popc(__vcmpeq4(reinterpret_cast<const uint32_t*>(sg)[i] & 0x7f7f7f7fu, 0x03030303u)) >> 3;
+        int h = 0;                                            // compute_permitted_area: count 'H' (occupancy bit ignored)
+        warp_for(p.GS >> 4, lane, [&](int i) {
+            uint4 v = reinterpret_cast<const uint4*>(sg)[i];
+            v.x &= 0x7f7f7f7fu; v.y &= 0x7f7f7f7fu; v.z &= 0x7f7f7f7fu; v.w &= 0x7f7f7f7fu;
+            h += count_eq16(v, 0x03030303u);
+        });
         h = __reduce_add_sync(kFull, h);
         tA = __ldg(&m->thr_apple[h]);
         tW = __ldg(&m->thr_waste[h]);
@@ -318,88 +339,153 @@ __device__ __forceinline__ void st_row32(uint8_t* dst, const uint32_t* w) {     
                  :: "l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
-// Row gather.  Two zero-padded copies of the map are kept in shared memory as colour INDICES:
-//   M  [padded row][padded col]  (pitch PWp)  and  MT [padded col][padded row]  (pitch PHp),
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // raw PRMT: no selector masking
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// Row gather from NIBBLE-PACKED padded index maps.
+// Four zero-padded copies of the map live in shared memory as 4-bit colour indices (8 cells per word):
+//   M   [padded row][col]      MR  [padded row][W-1-col]      MT  [padded col][row]      MTR [padded col][H-1-row]
 // so that for every orientation an output row of the rotated egocentric window (np.rot90 k=1,3,0,2 for
-// LEFT, RIGHT, UP, DOWN; map_env.py:806-813) is ONE contiguous run of N bytes, ascending or descending:
-//   UP    out[y][:] = M [pr-V+y][pc-V ...]   ascending      DOWN  out[y][:] = M [pr+V-y][pc+V ...]  descending
-//   LEFT  out[y][:] = MT[pc+V-y][pr-V ...]   ascending      RIGHT out[y][:] = MT[pc-V+y][pr+V ...]  descending
-// A lane owns one (agent, y) output row: WR+1 aligned 32-bit loads, one PRMT per word to realign/reverse,
-// then the 8-entry colour LUT is applied to 4 pixels at a time with PRMT (selector = 4 index nibbles),
-// one PRMT per colour plane, and the finished row leaves the SM as one 32-byte (or 16-byte) global store
-// per plane.  Indices: 0-5 cell codes, 6 outside the map, 7 agent.
-template <int WR_T>
-__device__ __forceinline__ void gather_rows(const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane, uint32_t apack) {
-    const int WR = WR_T > 0 ? WR_T : (p.RP >> 2);
-    const uint32_t* mw = reinterpret_cast<const uint32_t*>(pmap);
-    const uint32_t lastmask = 0xffffffffu >> (8 * (4 * WR - p.N));
-    const uint32_t tr0 = p.lut8[0], tr1 = p.lut8[1], tg0 = p.lut8[2], tg1 = p.lut8[3], tb0 = p.lut8[4], tb1 = p.lut8[5];
-    const int units = p.n * p.N, iters = (units + 31) >> 5;
-    for (int it = 0; it < iters; ++it) {
-        const int u = it * 32 + lane;
-        const bool valid = u < units;
-        const int al = valid ? (int)(((uint32_t)u * p.invN20) >> 20) : 0;
-        const int y = u - al * p.N;
-        const uint32_t ap = __shfl_sync(kFull, apack, al);
-        if (!valid) continue;
-        const int pr = ap & 1023, pc = (ap >> 10) & 1023, o = ap >> 20;
-        const bool isMT = o < 2, desc = o & 1;
-        const int pitch = isMT ? p.PHp : p.PWp;
-        const int major = isMT ? pc : pr, minor = isMT ? pr : pc;
-        const int rowoff = (desc != isMT) ? p.V - y : y - p.V;
-        const int s0 = (isMT ? p.off_MT : p.off_M) + (major + rowoff) * pitch + minor + (desc ? p.V : -p.V);
-        const int sh = s0 & 3, ds = desc ? -1 : 1;
-        // PRMT selectors that realign (ascending) or realign + reverse (descending) a 4-byte window
-        const uint32_t sel = desc ? (uint32_t)((0x0123701267015670ull >> (16 * sh)) & 0xffffu) : (0x3210u + 0x1111u * sh);
-        int wi = s0 >> 2;
-        uint32_t prev = mw[wi];
-        uint8_t* dst = gobs + al * p.AS + y * p.RP;
-        uint32_t R[WR_T > 0 ? WR_T : 1], Gc[WR_T > 0 ? WR_T : 1], Bl[WR_T > 0 ? WR_T : 1];
+// LEFT, RIGHT, UP, DOWN; map_env.py:806-813) is ONE ascending run of N nibbles:
+//   UP    out[y][:] = M  [r-V+y][c-V ...]      DOWN  out[y][:] = MR [r+V-y][(W-1-c)-V ...]
+//   LEFT  out[y][:] = MT [c+V-y][r-V ...]      RIGHT out[y][:] = MTR[c-V+y][(H-1-r)-V ...]
+// A lane owns one (agent, y) output row: it loads the <=5 words holding the run, funnel-shifts them to
+// pixel 0 (SHF), and every 16 bits of the result ARE the PRMT selector that looks 4 pixels up in the
+// 8-entry colour LUT held in two registers per plane.  The finished row leaves the SM as one 32-byte
+// (st.global.v8.b32 -> STG.E.ENL2.256) or 16-byte store per plane.  Indices: 0-5 cell codes, 6 outside, 7 agent.
+template <int OCT_T>
+struct RowUnit {                                              // one (agent, y) output row in flight
+    uint32_t L[OCT_T > 0 ? OCT_T + 1 : 1];
+    const uint32_t* w;
+    uint8_t* dst;
+    uint32_t sh;
+    bool valid;
+};
+
+template <int OCT_T>
+__device__ __forceinline__ void fetch_row(const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane, int it, int units,
+                                          uint32_t abase_sh, int astep, RowUnit<OCT_T>& U) {
+    const int u = it * 32 + lane;
+    U.valid = u < units;
+    const int al = U.valid ? (int)(((uint32_t)u * p.invN20) >> 20) : 0;
+    const int y = u - al * p.N;
+    const uint32_t ab = __shfl_sync(kFull, abase_sh, al);
+    const int as = __shfl_sync(kFull, astep, al);
+    U.w = reinterpret_cast<const uint32_t*>(pmap + (ab & 0xffffu) + (U.valid ? y * as : 0));
+    U.sh = ab >> 16;
+    U.dst = gobs + al * p.AS + y * p.RP;
+    if constexpr (OCT_T > 0) {
 #pragma unroll
-        for (int k = 0; k < WR; ++k) {
-            wi += ds;
-            const uint32_t cur = mw[wi];
-            const uint32_t x = __byte_perm(prev, cur, sel);        // 4 colour indices, one per byte
-            prev = cur;
-            const uint32_t t = x | (x >> 4);
-            const uint32_t s16 = __byte_perm(t, 0u, 0x4420);       // -> 4 nibbles = PRMT selector
-            uint32_t r = __byte_perm(tr0, tr1, s16), g = __byte_perm(tg0, tg1, s16), b = __byte_perm(tb0, tb1, s16);
-            if (k == WR - 1) { r &= lastmask; g &= lastmask; b &= lastmask; }
-            if (WR_T > 0) { R[k] = r; Gc[k] = g; Bl[k] = b; }
-            else {
-                *reinterpret_cast<uint32_t*>(dst + 4 * k) = r;
-                *reinterpret_cast<uint32_t*>(dst + p.PS + 4 * k) = g;
-                *reinterpret_cast<uint32_t*>(dst + 2 * p.PS + 4 * k) = b;
-            }
+        for (int k = 0; k <= OCT_T; ++k) U.L[k] = U.w[k];     // always in bounds: invalid lanes read agent 0's row 0
+    }
+}
+
+template <int OCT_T>
+__device__ __forceinline__ void emit_row(const KParams& p, const RowUnit<OCT_T>& U, uint32_t lastmask) {
+    if (!U.valid) return;
+    const uint32_t sh = U.sh;
+    if constexpr (OCT_T > 0) {
+        uint32_t v[2 * OCT_T];
+#pragma unroll
+        for (int k = 0; k < OCT_T; ++k) { v[2 * k] = __funnelshift_r(U.L[k], U.L[k + 1], sh); v[2 * k + 1] = v[2 * k] >> 16; }
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {                      // one colour plane at a time: 2*OCT PRMTs, then one wide store
+            const uint32_t t0 = p.lut8[2 * pl], t1 = p.lut8[2 * pl + 1];
+            uint32_t o[2 * OCT_T];
+#pragma unroll
+            for (int k = 0; k < 2 * OCT_T; ++k) o[k] = prmt(t0, t1, v[k]);
+            o[2 * OCT_T - 1] &= lastmask;
+            if (OCT_T == 4) st_row32(U.dst + pl * p.PS, o);
+            else *reinterpret_cast<uint4*>(U.dst + pl * p.PS) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        if (WR_T == 8) { st_row32(dst, R); st_row32(dst + p.PS, Gc); st_row32(dst + 2 * p.PS, Bl); }
-        else if (WR_T == 4) {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(R[0], R[1], R[2], R[3]);
-            *reinterpret_cast<uint4*>(dst + p.PS) = make_uint4(Gc[0], Gc[1], Gc[2], Gc[3]);
-            *reinterpret_cast<uint4*>(dst + 2 * p.PS) = make_uint4(Bl[0], Bl[1], Bl[2], Bl[3]);
+    } else {
+        const int WR = p.RP >> 2, OCT = (WR + 1) >> 1;
+        uint32_t prev = U.w[0];
+        for (int k = 0; k < OCT; ++k) {
+            const uint32_t cur = U.w[k + 1];
+            uint32_t v = __funnelshift_r(prev, cur, sh);
+            prev = cur;
+            for (int hlf = 0; hlf < 2; ++hlf, v >>= 16) {
+                const int wd = 2 * k + hlf;
+                if (wd >= WR) break;
+                const uint32_t m = wd == WR - 1 ? lastmask : 0xffffffffu;
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl)
+                    *reinterpret_cast<uint32_t*>(U.dst + pl * p.PS + 4 * wd) = prmt(p.lut8[2 * pl], p.lut8[2 * pl + 1], v) & m;
+            }
         }
     }
 }
 
-// Builds one padded index map word by word: dest word j of padded row `row` holds source cells
-// base + (4j - V + k) * step, k = 0..3 (step 1: M from grid rows, step W: MT from grid columns).
-__device__ __forceinline__ void build_map(const KParams& p, const uint8_t* sg, uint8_t* map, int lane,
-                                          int rows, int len, int pitch, int row_stride, int step, uint32_t inv_nw20) {
-    const int w0 = p.V >> 2, nw = ((p.V + len - 1) >> 2) - w0 + 1;
-    const int total = rows * nw;
-    for (int i = lane; i < total; i += 32) {
-        const int row = (int)(((uint32_t)i * inv_nw20) >> 20), j = i - row * nw + w0;
-        const int e0 = 4 * j - p.V;                           // index along the row of the first byte of this word
-        const uint8_t* src = sg + row * row_stride + e0 * step;
-        uint32_t w = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int e = e0 + k;
-            const uint32_t v = (e >= 0 && e < len) ? (uint32_t)src[k * step] : 6u;
-            w |= v << (8 * k);
-        }
-        *reinterpret_cast<uint32_t*>(map + (row + p.V) * pitch + 4 * j) = w;
+template <int OCT_T>
+__device__ __forceinline__ void gather_rows(const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane,
+                                            uint32_t abase_sh, int astep) {
+    const int WR = p.RP >> 2;
+    const uint32_t lastmask = 0xffffffffu >> (8 * (4 * WR - p.N));
+    const int units = p.n * p.N, iters = (units + 31) >> 5;
+    RowUnit<OCT_T> cur, nxt;
+    fetch_row<OCT_T>(p, pmap, gobs, lane, 0, units, abase_sh, astep, cur);
+    for (int it = 0; it < iters; ++it) {                      // software pipeline: row it+1 is fetched while row it is emitted
+        if (it + 1 < iters) fetch_row<OCT_T>(p, pmap, gobs, lane, it + 1, units, abase_sh, astep, nxt);
+        emit_row<OCT_T>(p, cur, lastmask);
+        cur = nxt;
     }
+}
+
+// Nibble-packed padded maps, built one aligned 32-bit word (8 cells) at a time.  Map cells start at nibble
+// LPn (V rounded up to 8) of a padded row, so only the last word of a row needs its tail set to "outside".
+// Source contiguous along the run (M, and MR when `mirror`).
+__device__ __forceinline__ void build_rowmap(const KParams& p, const uint8_t* sg, uint8_t* map, int lane, bool mirror) {
+    const uint32_t* sgw = reinterpret_cast<const uint32_t*>(sg);
+    const int total = p.H * p.nw8M;
+    for (int i = lane; i < total; i += 32) {
+        const int r = (int)(((uint32_t)i * p.invMW20) >> 20), j = i - r * p.nw8M;
+        uint32_t x0, x1;
+        if (!mirror) {
+            const int sb = r * p.W + 8 * j, wi = sb >> 2;
+            const uint32_t sel = 0x3210u + 0x1111u * (sb & 3);
+            const uint32_t a0 = sgw[wi], a1 = sgw[wi + 1], a2 = sgw[wi + 2];
+            x0 = prmt(a0, a1, sel); x1 = prmt(a1, a2, sel);
+        } else {
+            const int sb = r * p.W + p.W - 1 - 8 * j, wi = sb >> 2;          // highest source byte first
+            const uint32_t sel = (uint32_t)((0x0123701267015670ull >> (16 * (sb & 3))) & 0xffffu);
+            const uint32_t a0 = sgw[wi], a1 = sgw[max(wi - 1, 0)], a2 = sgw[max(wi - 2, 0)];
+            x0 = prmt(a0, a1, sel); x1 = prmt(a1, a2, sel);
+        }
+        uint32_t w = prmt(x0 | (x0 >> 4), x1 | (x1 >> 4), 0x6420);            // 8 bytes -> 8 nibbles
+        if (j == p.nw8M - 1) w = (w & p.maskM8) | (0x66666666u & ~p.maskM8);
+        *reinterpret_cast<uint32_t*>(map + (r + p.V) * p.pitchM + (p.LPn >> 1) + 4 * j) = w;
+    }
+}
+// Source strided by W (MT, and MTR when `mirror`).
+__device__ __forceinline__ void build_colmap(const KParams& p, const uint8_t* sg, uint8_t* map, int lane, bool mirror) {
+    const int total = p.W * p.nw8T;
+    for (int i = lane; i < total; i += 32) {
+        const int c = (int)(((uint32_t)i * p.invMTW20) >> 20), j = i - c * p.nw8T;
+        uint32_t b[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                          // rows past the map are clamped, then masked below
+            const int rr = mirror ? max(p.H - 1 - (8 * j + k), 0) : min(8 * j + k, p.H - 1);
+            b[k] = sg[rr * p.W + c];
+        }
+        const uint32_t y0 = b[0] | (b[1] << 4), y1 = b[2] | (b[3] << 4), y2 = b[4] | (b[5] << 4), y3 = b[6] | (b[7] << 4);
+        uint32_t w = prmt(prmt(y0, y1, 0x0040), prmt(y2, y3, 0x0040), 0x5410);
+        if (j == p.nw8T - 1) w = (w & p.maskT8) | (0x66666666u & ~p.maskT8);
+        *reinterpret_cast<uint32_t*>(map + (c + p.V) * p.pitchT + (p.LPn >> 1) + 4 * j) = w;
+    }
+}
+
+// "outside the map" everywhere (utility_funcs.py:58-116 without np.pad); issued while the state loads are in flight
+__device__ __forceinline__ void fill_outside(const KParams& p, uint8_t* pmap, int lane) {
+    const uint4 v6 = make_uint4(0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u);
+    uint4* q = reinterpret_cast<uint4*>(pmap);
+    const int n16 = p.PMS >> 4;
+    int i = lane;
+    for (; i + 96 < n16; i += 128) { q[i] = v6; q[i + 32] = v6; q[i + 64] = v6; q[i + 96] = v6; }
+    for (; i < n16; i += 32) q[i] = v6;
 }
 
 __device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
@@ -423,32 +509,45 @@ __device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint
     }
     if (!p.obs) return;
 
-    // zero-padded index maps (utility_funcs.py:58-116 without np.pad)
-    for (int i = lane; i < (p.PMS >> 4); i += 32)
-        reinterpret_cast<uint4*>(pmap)[i] = make_uint4(0x06060606u, 0x06060606u, 0x06060606u, 0x06060606u);
-    const int pr = r0 + p.V, pc = c0 + p.V;
-    const uint32_t apack = (uint32_t)pr | ((uint32_t)pc << 10) | ((uint32_t)ori << 20);
-    const bool needM = __ballot_sync(kFull, is_agent && ori >= 2) != 0;
-    const bool needMT = __ballot_sync(kFull, is_agent && ori < 2) != 0;
+    // the maps were pre-filled with "outside the map" at kernel start (fill_outside); now the cells, then the agents
+    // per agent: which map, first word of its window row 0, row step, funnel shift   (o: 0 LEFT 1 RIGHT 2 UP 3 DOWN)
+    const bool colmap = ori < 2, mirror = (ori == 1) || (ori == 3);
+    const int rowc = colmap ? c0 : r0;                        // coordinate that selects the map row
+    const int runc = colmap ? (mirror ? p.H - 1 - r0 : r0) : (mirror ? p.W - 1 - c0 : c0);   // coordinate along the run
+    const int pitch = colmap ? p.pitchT : p.pitchM;
+    const bool down = (ori == 0) || (ori == 3);               // window row y walks towards smaller map rows
+    const int s = p.LPn + runc - p.V;
+    const uint32_t abase_sh = (uint32_t)(p.off_map[ori] + (rowc + (down ? 2 * p.V : 0)) * pitch + ((s >> 3) << 2))
+                              | ((uint32_t)((s & 7) * 4) << 16);
+    const int astep = down ? -pitch : pitch;
+    const unsigned omask = (__ballot_sync(kFull, is_agent && ori == 0) ? 1u : 0u) | (__ballot_sync(kFull, is_agent && ori == 1) ? 2u : 0u) |
+                           (__ballot_sync(kFull, is_agent && ori == 2) ? 4u : 0u) | (__ballot_sync(kFull, is_agent && ori == 3) ? 8u : 0u);
     __syncwarp();
-    uint8_t* M = pmap + p.off_M;
-    uint8_t* MT = pmap + p.off_MT;
-    if (needM) build_map(p, sg, M, lane, p.H, p.W, p.PWp, p.W, 1, p.invMW20);
-    if (needMT) build_map(p, sg, MT, lane, p.W, p.H, p.PHp, 1, p.W, p.invMTW20);
+    if (omask & 4u) build_rowmap(p, sg, pmap + p.off_map[2], lane, false);
+    if (omask & 8u) build_rowmap(p, sg, pmap + p.off_map[3], lane, true);
+    if (omask & 1u) build_colmap(p, sg, pmap + p.off_map[0], lane, false);
+    if (omask & 2u) build_colmap(p, sg, pmap + p.off_map[1], lane, true);
     __syncwarp();
-    if (top) { M[pr * p.PWp + pc] = 7; MT[pc * p.PHp + pr] = 7; }
+    if (top) {                                                // any cell code | 7 == 7: one atomic OR per map, no RMW race
+        const int nm = p.LPn + c0, nmr = p.LPn + p.W - 1 - c0, nt = p.LPn + r0, ntr = p.LPn + p.H - 1 - r0;
+        if (omask & 4u) atomicOr(reinterpret_cast<unsigned*>(pmap + p.off_map[2] + (r0 + p.V) * p.pitchM + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
+        if (omask & 8u) atomicOr(reinterpret_cast<unsigned*>(pmap + p.off_map[3] + (r0 + p.V) * p.pitchM + ((nmr >> 3) << 2)), 7u << (4 * (nmr & 7)));
+        if (omask & 1u) atomicOr(reinterpret_cast<unsigned*>(pmap + p.off_map[0] + (c0 + p.V) * p.pitchT + ((nt >> 3) << 2)), 7u << (4 * (nt & 7)));
+        if (omask & 2u) atomicOr(reinterpret_cast<unsigned*>(pmap + p.off_map[1] + (c0 + p.V) * p.pitchT + ((ntr >> 3) << 2)), 7u << (4 * (ntr & 7)));
+    }
     __syncwarp();
 
     uint8_t* gobs = p.obs + (size_t)env * p.ES;
-    if (p.RP == 32) gather_rows<8>(p, pmap, gobs, lane, apack);
-    else if (p.RP == 16) gather_rows<4>(p, pmap, gobs, lane, apack);
-    else gather_rows<0>(p, pmap, gobs, lane, apack);
+    if (p.RP == 32) gather_rows<4>(p, pmap, gobs, lane, abase_sh, astep);
+    else if (p.RP == 16) gather_rows<2>(p, pmap, gobs, lane, abase_sh, astep);
+    else gather_rows<0>(p, pmap, gobs, lane, abase_sh, astep);
     const int tail = p.AS - 3 * p.PS;                         // pad bytes per agent block (0 for the shipped views)
     if (tail) for (int i = lane; i < p.n * (tail >> 2); i += 32)
         *reinterpret_cast<uint32_t*>(gobs + (i / (tail >> 2)) * p.AS + 3 * p.PS + 4 * (i % (tail >> 2))) = 0u;
     if (!p.agents_uniform) {
         // full-colour scheme: every visible agent is re-painted with its own colour (after the row stores)
         __syncwarp();
+        const uint32_t apack = (uint32_t)r0 | ((uint32_t)c0 << 10) | ((uint32_t)ori << 20);
         const int pairs = p.n * p.n, iters = (pairs + 31) >> 5;
         for (int it = 0; it < iters; ++it) {
             const int q = it * 32 + lane;
@@ -472,7 +571,7 @@ __device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint
 
 // ------------------------------------------------------------------ the kernel
 template <int MODE>
-__global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t lut_s[16];
     if (threadIdx.x < 16) lut_s[threadIdx.x] = p.lut[threadIdx.x];
@@ -486,27 +585,33 @@ __global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant_
     uint8_t* pmap = sg + p.off_pmap;
     const bool is_agent = lane < p.n;
     const uint32_t gid = p.gid_base + (uint32_t)env;
-    uint32_t tick = p.tick[env];
+    // every global load of the step is issued up front; the map pre-fill below overlaps their latency
+    const uint32_t tick = p.tick[env];
+    const int t_prev = MODE == MODE_STEP ? p.t[env] : 0;
+    const int act = (MODE == MODE_STEP && is_agent) ? (int)p.actions[(size_t)env * p.n + lane] : 255;
     int pos = -1 - lane, ori = 0, ep_ret = 0;
-
-    // stage the grid
-    if (MODE == MODE_RESET) {
-        for (int i = lane; i < (p.GS >> 4); i += 32)
-            reinterpret_cast<uint4*>(sg)[i] = __ldg(reinterpret_cast<const uint4*>(p.map->base_grid) + i);
-    } else {
-        const uint4* src = reinterpret_cast<const uint4*>(p.grid + (size_t)env * p.GS);
-        for (int i = lane; i < (p.GS >> 4); i += 32) reinterpret_cast<uint4*>(sg)[i] = src[i];
-        if (is_agent) {
-            const uint32_t a = p.agent[(size_t)env * p.NA + lane];
-            pos = (int)(a & 0xff) * p.W + (int)((a >> 8) & 0xff);
-            ori = (int)((a >> 16) & 3);
-            ep_ret = p.ep_ret[(size_t)env * p.NA + lane];
-        }
+    uint32_t a_rec = 0;
+    if (MODE != MODE_RESET && is_agent) {
+        a_rec = p.agent[(size_t)env * p.NA + lane];
+        ep_ret = p.ep_ret[(size_t)env * p.NA + lane];
+    }
+    const int n16 = p.GS >> 4;
+    uint4 g0 = make_uint4(0, 0, 0, 0);
+    {
+        const uint4* src = MODE == MODE_RESET ? reinterpret_cast<const uint4*>(p.map->base_grid)
+                                              : reinterpret_cast<const uint4*>(p.grid + (size_t)env * p.GS);
+        if (lane < n16) g0 = src[lane];
+        if (p.obs) fill_outside(p, pmap, lane);
+        if (lane < n16) reinterpret_cast<uint4*>(sg)[lane] = g0;
+        for (int i = lane + 32; i < n16; i += 32) reinterpret_cast<uint4*>(sg)[i] = src[i];
+    }
+    if (MODE != MODE_RESET && is_agent) {
+        pos = (int)(a_rec & 0xff) * p.W + (int)((a_rec >> 8) & 0xff);
+        ori = (int)((a_rec >> 16) & 3);
     }
     __syncwarp();
 
     if (MODE == MODE_STEP) {
-        const int act = is_agent ? (int)p.actions[(size_t)env * p.n + lane] : 255;
         int reward = 0, clean_num = 0;
         update_moves(p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
         // consume in index order: the lowest index on a cell eats the apple (253-256); mark occupancy
@@ -520,19 +625,13 @@ __global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant_
         __syncwarp();
         beams(p, sg, lane, is_agent, act, pos, ori, reward, clean_num);                     // 259-260
         spawn(p, sg, lane, env, gid, tick);                                                 // 263
-        // apple density numerator (291-292): after consume + spawn no apple lies under an agent
-        int apples = 0;
-        for (int i = lane; i < (p.GS >> 2); i += 32)
-            apples += __popc(__vcmpeq4(reinterpret_cast<const uint32_t*>(sg)[i], 0x02020202u)) >> 3;
-        apples = __reduce_add_sync(kFull, apples);
-        const int t = p.t[env] + 1;
+        const int t = t_prev + 1;
         if (is_agent) {
             p.reward[(size_t)env * p.n + lane] = (int8_t)reward;
             p.clean[(size_t)env * p.n + lane] = (uint8_t)clean_num;
             ep_ret += reward;                                                               // 885-888
         }
         if (lane == 0) {
-            p.apple_cnt[env] = (uint16_t)apples;
             p.done[env] = t >= p.episode_limit;                                             // 890-894
             p.t[env] = t;
             p.tick[env] = tick + 1;
@@ -571,7 +670,17 @@ __global__ void __launch_bounds__(kWarps * 32) ssd_kernel(const __grid_constant_
         if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
         __syncwarp();
         uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * p.GS);
-        for (int i = lane; i < (p.GS >> 4); i += 32) dst[i] = reinterpret_cast<const uint4*>(sg)[i];
+        int apples = 0;
+        warp_for(p.GS >> 4, lane, [&](int i) {
+            const uint4 v = reinterpret_cast<const uint4*>(sg)[i];
+            dst[i] = v;
+            if (MODE == MODE_STEP) apples += count_eq16(v, 0x02020202u);
+        });
+        if (MODE == MODE_STEP) {
+            // apple density numerator (map_env.py:291-292): after consume + spawn no apple lies under an agent
+            apples = __reduce_add_sync(kFull, apples);
+            if (lane == 0) p.apple_cnt[env] = (uint16_t)apples;
+        }
         if (is_agent) {
             const int r = (int)(((uint32_t)pos * p.invW20) >> 20);
             p.agent[(size_t)env * p.NA + lane] = (uint32_t)r | ((uint32_t)(pos - r * p.W) << 8) | ((uint32_t)ori << 16);
@@ -729,12 +838,18 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     k.kind = cfg->kind; k.B = cfg->n_envs; k.n = n; k.H = H; k.W = W; k.G = G; k.V = V; k.N = 2 * V + 1; k.NN = k.N * k.N;
     k.GS = round_up(G, 16); k.NA = round_up(n, 4);
     k.RP = round_up(k.N, 4); k.PS = k.N * k.RP; k.AS = round_up(3 * k.PS, 16); k.ES = n * k.AS;
-    // padded index maps; word pitch kept odd so that lanes gathering consecutive rows hit distinct banks
-    k.PWp = round_up(W + 2 * V, 4); if (((k.PWp >> 2) & 1) == 0) k.PWp += 4;
-    k.PHp = round_up(H + 2 * V, 4); if (((k.PHp >> 2) & 1) == 0) k.PHp += 4;
-    k.off_M = 16;
-    k.off_MT = k.off_M + round_up((H + 2 * V) * k.PWp, 16) + 16;
-    k.PMS = k.off_MT + round_up((W + 2 * V) * k.PHp, 16) + 16;
+    // nibble-packed padded maps; word pitch kept odd so that lanes gathering consecutive rows hit distinct banks
+    k.LPn = round_up(V, 8); k.nw8M = (W + 7) / 8; k.nw8T = (H + 7) / 8;
+    k.maskM8 = (W & 7) ? (1u << (4 * (W & 7))) - 1u : 0xffffffffu;
+    k.maskT8 = (H & 7) ? (1u << (4 * (H & 7))) - 1u : 0xffffffffu;
+    {
+        int wm = (k.LPn + W + V + 7) / 8; if (wm < k.LPn / 8 + k.nw8M) wm = k.LPn / 8 + k.nw8M; if ((wm & 1) == 0) ++wm;
+        int wt = (k.LPn + H + V + 7) / 8; if (wt < k.LPn / 8 + k.nw8T) wt = k.LPn / 8 + k.nw8T; if ((wt & 1) == 0) ++wt;
+        k.pitchM = 4 * wm; k.pitchT = 4 * wt;
+        const int szM = round_up((H + 2 * V) * k.pitchM, 16) + 16, szT = round_up((W + 2 * V) * k.pitchT, 16) + 16;
+        k.off_map[0] = 0; k.off_map[1] = szT; k.off_map[2] = 2 * szT; k.off_map[3] = 2 * szT + szM;
+        k.PMS = 2 * szT + 2 * szM + 16;
+    }
     k.episode_limit = cfg->episode_limit; k.fire_cost = cfg->fire_cost; k.hit_penalty = cfg->hit_penalty;
     k.beam_len = cfg->beam_len; k.n_actions = cfg->kind == SSD_KIND_CLEANUP ? 9 : 8;
     k.n_apple = na; k.n_waste = nw; k.n_spawn = ns; k.n_apple4 = (na + 3) / 4; k.n_waste2 = (nw + 1) / 2;
@@ -753,11 +868,8 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     }
     if (k.invN20 == 0 || k.invW20 == 0 || k.n_apple4 > 32 * 16) { delete hm; delete h; return SSD_ERR_INVALID; }
 
-    {
-        const int nwM = ((V + W - 1) >> 2) - (V >> 2) + 1, nwMT = ((V + H - 1) >> 2) - (V >> 2) + 1;
-        k.invMW20 = magic20(nwM, H * nwM + 32); k.invMTW20 = magic20(nwMT, W * nwMT + 32);
-        if (k.invMW20 == 0 || k.invMTW20 == 0) { delete hm; delete h; return SSD_ERR_INVALID; }
-    }
+    k.invMW20 = magic20(k.nw8M, H * k.nw8M + 32); k.invMTW20 = magic20(k.nw8T, W * k.nw8T + 32);
+    if (k.invMW20 == 0 || k.invMTW20 == 0 || k.PMS >= 60000) { delete hm; delete h; return SSD_ERR_INVALID; }
     k.off_pmap = k.GS;
     k.smem_per_warp = k.off_pmap + k.PMS;
     h->smem_bytes = (size_t)kWarps * k.smem_per_warp;

@@ -61,5 +61,62 @@ for r in rows:
         lines.append(r)
 ie, smp = hdr.index("Instructions Executed"), hdr.index("# Samples")
 print("top source lines by warp-instructions (per env-step):")
-for r in sorted(lines, key=lambda r: -int(r[ie] or 0))[:45]:
-    print("  L%-4s %8.1f  smp %-4s %s" % (r[0], int(r[ie]) / n_env, r[smp], r[1].strip()[:110]))
+def _n(r):
+    try:
+        return int(r[ie] or 0)
+    except ValueError:
+        return 0
+
+
+for r in sorted(lines, key=lambda r: -_n(r))[:45]:
+    print("  L%-4s %8.1f  smp %-4s %s" % (r[0], _n(r) / n_env, r[smp], r[1].strip()[:110]))
+
+# per function (by source line ranges found from markers in the .cu file)
+import re
+src_path = hdr and rows[0][1] if rows and rows[0] and rows[0][0] == "File Path" else None
+marks = []
+try:
+    text = open(src_path).read().splitlines()
+    for i, l in enumerate(text, 1):
+        m = re.match(r"(?:template <[^>]*>\s*)?__device__ __forceinline__ \w[\w<>]* (\w+)\(|__global__ void .*? (\w+)\(", l)
+        if m:
+            marks.append((i, m.group(1) or m.group(2)))
+except Exception:
+    marks = []
+if marks:
+    marks.append((10 ** 9, "end"))
+    agg = Counter()
+    for r in lines:
+        try:
+            ln = int(r[0])
+        except ValueError:
+            continue
+        name = "pre"
+        for (a, nm), (b, _) in zip(marks, marks[1:]):
+            if a <= ln < b:
+                name = nm
+        agg[name] += _n(r)
+    print("warp-instructions per env-step by function:")
+    for k, v in agg.most_common():
+        print("  %-18s %8.1f" % (k, v / n_env))
+
+print("top source lines by stall samples:")
+tot_s = sum(int(r[smp] or 0) for r in lines if (r[smp] or "0").isdigit())
+for r in sorted(lines, key=lambda r: -(int(r[smp]) if (r[smp] or "0").isdigit() else 0))[:25]:
+    print("  L%-4s smp %-5s (%4.1f%%) instr/env %7.1f  %s" % (r[0], r[smp], 100.0 * int(r[smp]) / max(tot_s, 1), _n(r) / n_env, r[1].strip()[:100]))
+if marks:
+    aggs = Counter()
+    for r in lines:
+        try:
+            ln = int(r[0]); sm_ = int(r[smp] or 0)
+        except ValueError:
+            continue
+        name = "pre"
+        for (a, nm), (b, _) in zip(marks, marks[1:]):
+            if a <= ln < b:
+                name = nm
+        aggs[name] += sm_
+    print("stall samples by function (share of warp residency time):")
+    for k, v in aggs.most_common():
+        if v:
+            print("  %-18s %6d  %5.1f%%" % (k, v, 100.0 * v / max(tot_s, 1)))
