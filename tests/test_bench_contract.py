@@ -1,0 +1,50 @@
+"""bench.py prints ONE JSON line with the contract's keys (CPU arm here; CUDA arm under -m gpu)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def _run(args, env=None):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                       env={**os.environ, **(env or {})}, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    return lines
+
+
+def test_reference_arm_line():
+    lines = _run(["--impl", "reference", "--steps", "3", "--warmup", "1", "--workload", "cleanup3_b4096", "--envs", "64"])
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["unit"] == "agent-steps/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["dtype"] == "u8" and d["data"] == "synthetic"
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    assert _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--envs", "64"], env={"RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+@pytest.mark.gpu
+def test_cuda_arm_line():
+    lines = _run(["--steps", "300", "--warmup", "20", "--envs", "512", "--e2e-steps", "5"])
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 300 and d["scaling"] == "weak" and d["dtype"] == "u8"
+    assert d["gpu_launches"] >= 300
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 512 * 5 and e["d2h_bytes_per_step"] > 512 * 5 * 3 * 31 * 31 and 0 < e["value"] < d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
