@@ -66,6 +66,92 @@ struct KParams {
     const uint32_t* d_spawnkey; const uint8_t* d_rot;
 };
 
+
+// ------------------------------------------------------------------ geometry
+// Everything that follows from (kind, H, W, V).  Computed by ONE constexpr function used by the host
+// (ssd_create) and, for the reference's shipped maps, at compile time by the kernels (GeoS), so that index
+// arithmetic folds into immediates; any other geometry runs the same code on runtime values (GeoD).
+struct GeoVals {
+    int kind, H, W, V, G, GS, N, NN, RP, PS, AS, LPn, nw8M, nw8T, pitchM, pitchT, off0, off1, off2, off3, PMS;
+    uint32_t maskM8, maskT8;
+};
+__host__ __device__ constexpr int cround_up(int v, int m) { return (v + m - 1) / m * m; }
+__host__ __device__ constexpr GeoVals make_geo(int kind, int H, int W, int V) {
+    GeoVals g{};
+    g.kind = kind; g.H = H; g.W = W; g.V = V; g.G = H * W; g.GS = cround_up(H * W, 16);
+    g.N = 2 * V + 1; g.NN = g.N * g.N; g.RP = cround_up(g.N, 4); g.PS = g.N * g.RP; g.AS = cround_up(3 * g.PS, 16);
+    // nibble-packed padded maps; word pitch kept odd so that lanes gathering consecutive rows hit distinct banks
+    g.LPn = cround_up(V, 8); g.nw8M = (W + 7) / 8; g.nw8T = (H + 7) / 8;
+    g.maskM8 = (W & 7) ? (1u << (4 * (W & 7))) - 1u : 0xffffffffu;
+    g.maskT8 = (H & 7) ? (1u << (4 * (H & 7))) - 1u : 0xffffffffu;
+    int wm = (g.LPn + W + V + 7) / 8; if (wm < g.LPn / 8 + g.nw8M) wm = g.LPn / 8 + g.nw8M; if ((wm & 1) == 0) ++wm;
+    int wt = (g.LPn + H + V + 7) / 8; if (wt < g.LPn / 8 + g.nw8T) wt = g.LPn / 8 + g.nw8T; if ((wt & 1) == 0) ++wt;
+    g.pitchM = 4 * wm; g.pitchT = 4 * wt;
+    const int szM = cround_up((H + 2 * V) * g.pitchM, 16) + 16, szT = cround_up((W + 2 * V) * g.pitchT, 16) + 16;
+    g.off0 = 0; g.off1 = szT; g.off2 = 2 * szT; g.off3 = 2 * szT + szM;     // index = orientation: MT, MTR, M, MR
+    g.PMS = 2 * szT + 2 * szM + 16;
+    return g;
+}
+
+template <int KIND_, int H_, int W_, int V_>
+struct GeoS {                                                 // compile-time geometry
+    static constexpr GeoVals v = make_geo(KIND_, H_, W_, V_);
+    __device__ __forceinline__ explicit GeoS(const KParams&) {}
+    __device__ __forceinline__ int kind() const { return v.kind; }
+    __device__ __forceinline__ int H() const { return v.H; }
+    __device__ __forceinline__ int W() const { return v.W; }
+    __device__ __forceinline__ int V() const { return v.V; }
+    __device__ __forceinline__ int G() const { return v.G; }
+    __device__ __forceinline__ int GS() const { return v.GS; }
+    __device__ __forceinline__ int N() const { return v.N; }
+    __device__ __forceinline__ int NN() const { return v.NN; }
+    __device__ __forceinline__ int RP() const { return v.RP; }
+    __device__ __forceinline__ int PS() const { return v.PS; }
+    __device__ __forceinline__ int AS() const { return v.AS; }
+    __device__ __forceinline__ int LPn() const { return v.LPn; }
+    __device__ __forceinline__ int nw8M() const { return v.nw8M; }
+    __device__ __forceinline__ int nw8T() const { return v.nw8T; }
+    __device__ __forceinline__ int pitchM() const { return v.pitchM; }
+    __device__ __forceinline__ int pitchT() const { return v.pitchT; }
+    __device__ __forceinline__ int PMS() const { return v.PMS; }
+    __device__ __forceinline__ uint32_t maskM8() const { return v.maskM8; }
+    __device__ __forceinline__ uint32_t maskT8() const { return v.maskT8; }
+    __device__ __forceinline__ int off_map(int o) const { return o == 0 ? v.off0 : (o == 1 ? v.off1 : (o == 2 ? v.off2 : v.off3)); }
+    __device__ __forceinline__ int divW(int x) const { return (int)((unsigned)x / (unsigned)v.W); }
+    __device__ __forceinline__ int divN(int x) const { return (int)((unsigned)x / (unsigned)v.N); }
+    __device__ __forceinline__ int divMW(int x) const { return (int)((unsigned)x / (unsigned)v.nw8M); }
+    __device__ __forceinline__ int divMTW(int x) const { return (int)((unsigned)x / (unsigned)v.nw8T); }
+};
+
+struct GeoD {                                                 // runtime geometry (any wall-enclosed map)
+    const KParams& p;
+    __device__ __forceinline__ explicit GeoD(const KParams& p_) : p(p_) {}
+    __device__ __forceinline__ int kind() const { return p.kind; }
+    __device__ __forceinline__ int H() const { return p.H; }
+    __device__ __forceinline__ int W() const { return p.W; }
+    __device__ __forceinline__ int V() const { return p.V; }
+    __device__ __forceinline__ int G() const { return p.G; }
+    __device__ __forceinline__ int GS() const { return p.GS; }
+    __device__ __forceinline__ int N() const { return p.N; }
+    __device__ __forceinline__ int NN() const { return p.NN; }
+    __device__ __forceinline__ int RP() const { return p.RP; }
+    __device__ __forceinline__ int PS() const { return p.PS; }
+    __device__ __forceinline__ int AS() const { return p.AS; }
+    __device__ __forceinline__ int LPn() const { return p.LPn; }
+    __device__ __forceinline__ int nw8M() const { return p.nw8M; }
+    __device__ __forceinline__ int nw8T() const { return p.nw8T; }
+    __device__ __forceinline__ int pitchM() const { return p.pitchM; }
+    __device__ __forceinline__ int pitchT() const { return p.pitchT; }
+    __device__ __forceinline__ int PMS() const { return p.PMS; }
+    __device__ __forceinline__ uint32_t maskM8() const { return p.maskM8; }
+    __device__ __forceinline__ uint32_t maskT8() const { return p.maskT8; }
+    __device__ __forceinline__ int off_map(int o) const { return p.off_map[o]; }
+    __device__ __forceinline__ int divW(int x) const { return (int)(((uint32_t)x * p.invW20) >> 20); }
+    __device__ __forceinline__ int divN(int x) const { return (int)(((uint32_t)x * p.invN20) >> 20); }
+    __device__ __forceinline__ int divMW(int x) const { return (int)(((uint32_t)x * p.invMW20) >> 20); }
+    __device__ __forceinline__ int divMTW(int x) const { return (int)(((uint32_t)x * p.invMTW20) >> 20); }
+};
+
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                uint32_t k0, uint32_t k1) {
@@ -113,7 +199,8 @@ __device__ __forceinline__ int agent_colour_index(int i) {
 // ------------------------------------------------------------------ update_moves (map_env.py:477-661)
 // lanes < n hold one agent each: pos (cell index), ori, act.  Non-agent lanes carry unique
 // negative positions so they never match a cell.
-__device__ __forceinline__ void update_moves(const KParams& p, const uint8_t* __restrict__ sg, int lane, bool is_agent,
+template <class GEO>
+__device__ __forceinline__ void update_moves(const GEO& g, const KParams& p, const uint8_t* __restrict__ sg, int lane, bool is_agent,
                                              int act, int& pos, int& ori, int env, uint32_t gid, uint32_t tick) {
     // turns take effect immediately (map_env.py:509-511, 843-861)
     if (act == 5) ori = (0x0132 >> (4 * ori)) & 3;           // CW : LEFT->UP, RIGHT->DOWN, UP->RIGHT, DOWN->LEFT
@@ -130,7 +217,7 @@ __device__ __forceinline__ void update_moves(const KParams& p, const uint8_t* __
                                  (1u << 16) | (1u << 18) | (0u << 20) | (2u << 22) | (1u << 24) | (1u << 26) | (2u << 28) | (0u << 30);
         const int f = 2 * (ori * 4 + act);
         const int dr = (int)((kDr >> f) & 3u) - 1, dc = (int)((kDc >> f) & 3u) - 1;
-        const int q = pos + dr * p.W + dc;
+        const int q = pos + dr * g.W() + dc;
         prop = sg[q] == SSD_CELL_WALL ? pos : q;             // agent.py:111-119
     }
     unsigned in_moves = __ballot_sync(kFull, mover);
@@ -206,10 +293,11 @@ __device__ __forceinline__ void update_moves(const KParams& p, const uint8_t* __
 constexpr uint8_t kOcc = 0x80;
 
 // ------------------------------------------------------------------ beams (map_env.py:663-769)
-__device__ __forceinline__ void beams(const KParams& p, uint8_t* sg, int lane, bool is_agent,
+template <class GEO>
+__device__ __forceinline__ void beams(const GEO& g, const KParams& p, uint8_t* sg, int lane, bool is_agent,
                                       int act, int pos, int ori, int& reward, int& clean_num) {
     const bool fire = is_agent && act == 7;
-    const bool clean = is_agent && act == 8 && p.kind == SSD_KIND_CLEANUP;
+    const bool clean = is_agent && act == 8 && g.kind() == SSD_KIND_CLEANUP;
     if (fire) reward -= p.fire_cost;                          // agent.py:188-190, 239-241
     unsigned need = __ballot_sync(kFull, clean || (fire && p.hit_penalty != 0));
     while (need) {                                            // agent index order, map effects applied per agent (669-671)
@@ -220,7 +308,7 @@ __device__ __forceinline__ void beams(const KParams& p, uint8_t* sg, int lane, b
         // firing direction ORIENTATIONS[o] and its right-hand rotation (map_env.py:28-31, 840-841)
         const int dr = orii == 0 ? -1 : (orii == 1 ? 1 : 0), dc = orii == 2 ? -1 : (orii == 3 ? 1 : 0);
         const int rr = orii == 2 ? 1 : (orii == 3 ? -1 : 0), rc = orii == 0 ? -1 : (orii == 1 ? 1 : 0);
-        const int d = dr * p.W + dc, rs = rr * p.W + rc;
+        const int d = dr * g.W() + dc, rs = rr * g.W() + rc;
         int upd = -1, hit = -1;
         if (lane < 3) {                                       // the three parallel rays (728-730)
             int q = posi + (lane == 0 ? d : (lane == 1 ? rs : -rs));
@@ -253,12 +341,13 @@ __device__ __forceinline__ void beams(const KParams& p, uint8_t* sg, int lane, b
 }
 
 // ------------------------------------------------------------------ spawning (cleanup.py:165-204, harvest.py:92-122)
-__device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick) {
+template <class GEO>
+__device__ __forceinline__ void spawn(const GEO& g, const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick) {
     const MapDev* __restrict__ m = p.map;
     uint32_t tA = 1, tW = 0;
-    if (p.kind == SSD_KIND_CLEANUP) {
+    if (g.kind() == SSD_KIND_CLEANUP) {
         int h = 0;                                            // compute_permitted_area: count 'H' (occupancy bit ignored)
-        warp_for(p.GS >> 4, lane, [&](int i) {
+        warp_for(g.GS() >> 4, lane, [&](int i) {
             uint4 v = reinterpret_cast<const uint4*>(sg)[i];
             v.x &= 0x7f7f7f7fu; v.y &= 0x7f7f7f7fu; v.z &= 0x7f7f7f7fu; v.w &= 0x7f7f7f7fu;
             h += count_eq16(v, 0x03030303u);
@@ -283,15 +372,15 @@ __device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, int lane, i
                 const int v = sg[c];
                 if ((v & kOcc) || v == SSD_CELL_APPLE) continue;               // cleanup.py:171, harvest.py:105
                 uint32_t thr = tA;
-                if (p.kind == SSD_KIND_HARVEST) {
+                if (g.kind() == SSD_KIND_HARVEST) {
                     int cnt = 0;                                               // j^2+k^2 <= 2: the 3x3 block (harvest.py:107-116)
 #pragma unroll
                     for (int a = -1; a <= 1; ++a)
 #pragma unroll
-                        for (int b = -1; b <= 1; ++b) cnt += sg[c + a * p.W + b] == SSD_CELL_APPLE;
+                        for (int b = -1; b <= 1; ++b) cnt += sg[c + a * g.W() + b] == SSD_CELL_APPLE;
                     thr = p.thr_harvest[cnt < 3 ? cnt : 3];
                 }
-                const uint32_t u = p.d_uapple ? p.d_uapple[(size_t)env * p.G + c] : pick(r, q);
+                const uint32_t u = p.d_uapple ? p.d_uapple[(size_t)env * g.G() + c] : pick(r, q);
                 if (u < thr) decided |= 1ull << (it * 4 + q);
             }
         }
@@ -308,8 +397,8 @@ __device__ __forceinline__ void spawn(const KParams& p, uint8_t* sg, int lane, i
             for (int q = 0; q < 2; ++q) {
                 const uint32_t c = q ? pts.y : pts.x;
                 if (c == kNoPoint || (sg[c] & 0x7f) == SSD_CELL_WASTE) continue;   // cleanup.py:182
-                const uint32_t u = p.d_uwaste ? p.d_uwaste[(size_t)env * p.G + c] : (q ? r.z : r.x);
-                const uint32_t key = p.d_uwaste ? p.d_wkey[(size_t)env * p.G + c] : (q ? r.w : r.y);
+                const uint32_t u = p.d_uwaste ? p.d_uwaste[(size_t)env * g.G() + c] : (q ? r.z : r.x);
+                const uint32_t key = p.d_uwaste ? p.d_wkey[(size_t)env * g.G() + c] : (q ? r.w : r.y);
                 if (u < tW && (key < bk || (key == bk && c < bc))) { bk = key; bc = c; }
             }
         }
@@ -365,26 +454,26 @@ struct RowUnit {                                              // one (agent, y) 
     bool valid;
 };
 
-template <int OCT_T>
-__device__ __forceinline__ void fetch_row(const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane, int it, int units,
+template <int OCT_T, class GEO>
+__device__ __forceinline__ void fetch_row(const GEO& g, const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane, int it, int units,
                                           uint32_t abase_sh, int astep, RowUnit<OCT_T>& U) {
     const int u = it * 32 + lane;
     U.valid = u < units;
-    const int al = U.valid ? (int)(((uint32_t)u * p.invN20) >> 20) : 0;
-    const int y = u - al * p.N;
+    const int al = U.valid ? g.divN(u) : 0;
+    const int y = u - al * g.N();
     const uint32_t ab = __shfl_sync(kFull, abase_sh, al);
     const int as = __shfl_sync(kFull, astep, al);
     U.w = reinterpret_cast<const uint32_t*>(pmap + (ab & 0xffffu) + (U.valid ? y * as : 0));
     U.sh = ab >> 16;
-    U.dst = gobs + al * p.AS + y * p.RP;
+    U.dst = gobs + al * g.AS() + y * g.RP();
     if constexpr (OCT_T > 0) {
 #pragma unroll
         for (int k = 0; k <= OCT_T; ++k) U.L[k] = U.w[k];     // always in bounds: invalid lanes read agent 0's row 0
     }
 }
 
-template <int OCT_T>
-__device__ __forceinline__ void emit_row(const KParams& p, const RowUnit<OCT_T>& U, uint32_t lastmask) {
+template <int OCT_T, class GEO>
+__device__ __forceinline__ void emit_row(const GEO& g, const KParams& p, const RowUnit<OCT_T>& U, uint32_t lastmask) {
     if (!U.valid) return;
     const uint32_t sh = U.sh;
     if constexpr (OCT_T > 0) {
@@ -398,11 +487,11 @@ __device__ __forceinline__ void emit_row(const KParams& p, const RowUnit<OCT_T>&
 #pragma unroll
             for (int k = 0; k < 2 * OCT_T; ++k) o[k] = prmt(t0, t1, v[k]);
             o[2 * OCT_T - 1] &= lastmask;
-            if (OCT_T == 4) st_row32(U.dst + pl * p.PS, o);
-            else *reinterpret_cast<uint4*>(U.dst + pl * p.PS) = make_uint4(o[0], o[1], o[2], o[3]);
+            if (OCT_T == 4) st_row32(U.dst + pl * g.PS(), o);
+            else *reinterpret_cast<uint4*>(U.dst + pl * g.PS()) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     } else {
-        const int WR = p.RP >> 2, OCT = (WR + 1) >> 1;
+        const int WR = g.RP() >> 2, OCT = (WR + 1) >> 1;
         uint32_t prev = U.w[0];
         for (int k = 0; k < OCT; ++k) {
             const uint32_t cur = U.w[k + 1];
@@ -414,23 +503,23 @@ __device__ __forceinline__ void emit_row(const KParams& p, const RowUnit<OCT_T>&
                 const uint32_t m = wd == WR - 1 ? lastmask : 0xffffffffu;
 #pragma unroll
                 for (int pl = 0; pl < 3; ++pl)
-                    *reinterpret_cast<uint32_t*>(U.dst + pl * p.PS + 4 * wd) = prmt(p.lut8[2 * pl], p.lut8[2 * pl + 1], v) & m;
+                    *reinterpret_cast<uint32_t*>(U.dst + pl * g.PS() + 4 * wd) = prmt(p.lut8[2 * pl], p.lut8[2 * pl + 1], v) & m;
             }
         }
     }
 }
 
-template <int OCT_T>
-__device__ __forceinline__ void gather_rows(const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane,
+template <int OCT_T, class GEO>
+__device__ __forceinline__ void gather_rows(const GEO& g, const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane,
                                             uint32_t abase_sh, int astep) {
-    const int WR = p.RP >> 2;
-    const uint32_t lastmask = 0xffffffffu >> (8 * (4 * WR - p.N));
-    const int units = p.n * p.N, iters = (units + 31) >> 5;
+    const int WR = g.RP() >> 2;
+    const uint32_t lastmask = 0xffffffffu >> (8 * (4 * WR - g.N()));
+    const int units = p.n * g.N(), iters = (units + 31) >> 5;
     RowUnit<OCT_T> cur, nxt;
-    fetch_row<OCT_T>(p, pmap, gobs, lane, 0, units, abase_sh, astep, cur);
+    fetch_row<OCT_T>(g, p, pmap, gobs, lane, 0, units, abase_sh, astep, cur);
     for (int it = 0; it < iters; ++it) {                      // software pipeline: row it+1 is fetched while row it is emitted
-        if (it + 1 < iters) fetch_row<OCT_T>(p, pmap, gobs, lane, it + 1, units, abase_sh, astep, nxt);
-        emit_row<OCT_T>(p, cur, lastmask);
+        if (it + 1 < iters) fetch_row<OCT_T>(g, p, pmap, gobs, lane, it + 1, units, abase_sh, astep, nxt);
+        emit_row<OCT_T>(g, p, cur, lastmask);
         cur = nxt;
     }
 }
@@ -438,73 +527,77 @@ __device__ __forceinline__ void gather_rows(const KParams& p, const uint8_t* pma
 // Nibble-packed padded maps, built one aligned 32-bit word (8 cells) at a time.  Map cells start at nibble
 // LPn (V rounded up to 8) of a padded row, so only the last word of a row needs its tail set to "outside".
 // Source contiguous along the run (M, and MR when `mirror`).
-__device__ __forceinline__ void build_rowmap(const KParams& p, const uint8_t* sg, uint8_t* map, int lane, bool mirror) {
+template <class GEO>
+__device__ __forceinline__ void build_rowmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane, bool mirror) {
     const uint32_t* sgw = reinterpret_cast<const uint32_t*>(sg);
-    const int total = p.H * p.nw8M;
+    const int total = g.H() * g.nw8M();
     for (int i = lane; i < total; i += 32) {
-        const int r = (int)(((uint32_t)i * p.invMW20) >> 20), j = i - r * p.nw8M;
+        const int r = g.divMW(i), j = i - r * g.nw8M();
         uint32_t x0, x1;
         if (!mirror) {
-            const int sb = r * p.W + 8 * j, wi = sb >> 2;
+            const int sb = r * g.W() + 8 * j, wi = sb >> 2;
             const uint32_t sel = 0x3210u + 0x1111u * (sb & 3);
             const uint32_t a0 = sgw[wi], a1 = sgw[wi + 1], a2 = sgw[wi + 2];
             x0 = prmt(a0, a1, sel); x1 = prmt(a1, a2, sel);
         } else {
-            const int sb = r * p.W + p.W - 1 - 8 * j, wi = sb >> 2;          // highest source byte first
+            const int sb = r * g.W() + g.W() - 1 - 8 * j, wi = sb >> 2;          // highest source byte first
             const uint32_t sel = (uint32_t)((0x0123701267015670ull >> (16 * (sb & 3))) & 0xffffu);
             const uint32_t a0 = sgw[wi], a1 = sgw[max(wi - 1, 0)], a2 = sgw[max(wi - 2, 0)];
             x0 = prmt(a0, a1, sel); x1 = prmt(a1, a2, sel);
         }
         uint32_t w = prmt(x0 | (x0 >> 4), x1 | (x1 >> 4), 0x6420);            // 8 bytes -> 8 nibbles
-        if (j == p.nw8M - 1) w = (w & p.maskM8) | (0x66666666u & ~p.maskM8);
-        *reinterpret_cast<uint32_t*>(map + (r + p.V) * p.pitchM + (p.LPn >> 1) + 4 * j) = w;
+        if (j == g.nw8M() - 1) w = (w & g.maskM8()) | (0x66666666u & ~g.maskM8());
+        *reinterpret_cast<uint32_t*>(map + (r + g.V()) * g.pitchM() + (g.LPn() >> 1) + 4 * j) = w;
     }
 }
 // Source strided by W (MT, and MTR when `mirror`).
-__device__ __forceinline__ void build_colmap(const KParams& p, const uint8_t* sg, uint8_t* map, int lane, bool mirror) {
-    const int total = p.W * p.nw8T;
+template <class GEO>
+__device__ __forceinline__ void build_colmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane, bool mirror) {
+    const int total = g.W() * g.nw8T();
     for (int i = lane; i < total; i += 32) {
-        const int c = (int)(((uint32_t)i * p.invMTW20) >> 20), j = i - c * p.nw8T;
+        const int c = g.divMTW(i), j = i - c * g.nw8T();
         uint32_t b[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {                          // rows past the map are clamped, then masked below
-            const int rr = mirror ? max(p.H - 1 - (8 * j + k), 0) : min(8 * j + k, p.H - 1);
-            b[k] = sg[rr * p.W + c];
+            const int rr = mirror ? max(g.H() - 1 - (8 * j + k), 0) : min(8 * j + k, g.H() - 1);
+            b[k] = sg[rr * g.W() + c];
         }
         const uint32_t y0 = b[0] | (b[1] << 4), y1 = b[2] | (b[3] << 4), y2 = b[4] | (b[5] << 4), y3 = b[6] | (b[7] << 4);
         uint32_t w = prmt(prmt(y0, y1, 0x0040), prmt(y2, y3, 0x0040), 0x5410);
-        if (j == p.nw8T - 1) w = (w & p.maskT8) | (0x66666666u & ~p.maskT8);
-        *reinterpret_cast<uint32_t*>(map + (c + p.V) * p.pitchT + (p.LPn >> 1) + 4 * j) = w;
+        if (j == g.nw8T() - 1) w = (w & g.maskT8()) | (0x66666666u & ~g.maskT8());
+        *reinterpret_cast<uint32_t*>(map + (c + g.V()) * g.pitchT() + (g.LPn() >> 1) + 4 * j) = w;
     }
 }
 
 // "outside the map" everywhere (utility_funcs.py:58-116 without np.pad); issued while the state loads are in flight
-__device__ __forceinline__ void fill_outside(const KParams& p, uint8_t* pmap, int lane) {
+template <class GEO>
+__device__ __forceinline__ void fill_outside(const GEO& g, const KParams& p, uint8_t* pmap, int lane) {
     const uint4 v6 = make_uint4(0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u);
     uint4* q = reinterpret_cast<uint4*>(pmap);
-    const int n16 = p.PMS >> 4;
+    const int n16 = g.PMS() >> 4;
     int i = lane;
     for (; i + 96 < n16; i += 128) { q[i] = v6; q[i + 32] = v6; q[i + 64] = v6; q[i + 96] = v6; }
     for (; i < n16; i += 32) q[i] = v6;
 }
 
-__device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
+template <class GEO>
+__device__ __forceinline__ void render(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
                                        int lane, bool is_agent, int pos, int ori, int env) {
     const unsigned same = __match_any_sync(kFull, pos);
     const bool top = is_agent && lane == 31 - __clz(same);   // later index overwrites (map_env.py:370)
     int r0 = 0, c0 = 0;
-    if (is_agent) { r0 = (int)(((uint32_t)pos * p.invW20) >> 20); c0 = pos - r0 * p.W; }
+    if (is_agent) { r0 = g.divW(pos); c0 = pos - r0 * g.W(); }
 
     if (p.state_rgb) {                                        // get_state: unrotated full map (map_env.py:950-957)
-        uint8_t* out = p.state_rgb + (size_t)env * 3 * p.G;
-        for (int c = lane; c < p.G; c += 32) {
+        uint8_t* out = p.state_rgb + (size_t)env * 3 * g.G();
+        for (int c = lane; c < g.G(); c += 32) {
             const uint32_t rgb = lut_s[sg[c]];
-            out[c] = (uint8_t)rgb; out[p.G + c] = (uint8_t)(rgb >> 8); out[2 * p.G + c] = (uint8_t)(rgb >> 16);
+            out[c] = (uint8_t)rgb; out[g.G() + c] = (uint8_t)(rgb >> 8); out[2 * g.G() + c] = (uint8_t)(rgb >> 16);
         }
         __syncwarp();                                         // orders the agent overlay after the cell colours
         if (top) {
             const uint32_t rgb = lut_s[agent_colour_index(lane)];
-            out[pos] = (uint8_t)rgb; out[p.G + pos] = (uint8_t)(rgb >> 8); out[2 * p.G + pos] = (uint8_t)(rgb >> 16);
+            out[pos] = (uint8_t)rgb; out[g.G() + pos] = (uint8_t)(rgb >> 8); out[2 * g.G() + pos] = (uint8_t)(rgb >> 16);
         }
     }
     if (!p.obs) return;
@@ -513,37 +606,37 @@ __device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint
     // per agent: which map, first word of its window row 0, row step, funnel shift   (o: 0 LEFT 1 RIGHT 2 UP 3 DOWN)
     const bool colmap = ori < 2, mirror = (ori == 1) || (ori == 3);
     const int rowc = colmap ? c0 : r0;                        // coordinate that selects the map row
-    const int runc = colmap ? (mirror ? p.H - 1 - r0 : r0) : (mirror ? p.W - 1 - c0 : c0);   // coordinate along the run
-    const int pitch = colmap ? p.pitchT : p.pitchM;
+    const int runc = colmap ? (mirror ? g.H() - 1 - r0 : r0) : (mirror ? g.W() - 1 - c0 : c0);   // coordinate along the run
+    const int pitch = colmap ? g.pitchT() : g.pitchM();
     const bool down = (ori == 0) || (ori == 3);               // window row y walks towards smaller map rows
-    const int s = p.LPn + runc - p.V;
-    const uint32_t abase_sh = (uint32_t)(p.off_map[ori] + (rowc + (down ? 2 * p.V : 0)) * pitch + ((s >> 3) << 2))
+    const int s = g.LPn() + runc - g.V();
+    const uint32_t abase_sh = (uint32_t)(g.off_map(ori) + (rowc + (down ? 2 * g.V() : 0)) * pitch + ((s >> 3) << 2))
                               | ((uint32_t)((s & 7) * 4) << 16);
     const int astep = down ? -pitch : pitch;
     const unsigned omask = (__ballot_sync(kFull, is_agent && ori == 0) ? 1u : 0u) | (__ballot_sync(kFull, is_agent && ori == 1) ? 2u : 0u) |
                            (__ballot_sync(kFull, is_agent && ori == 2) ? 4u : 0u) | (__ballot_sync(kFull, is_agent && ori == 3) ? 8u : 0u);
     __syncwarp();
-    if (omask & 4u) build_rowmap(p, sg, pmap + p.off_map[2], lane, false);
-    if (omask & 8u) build_rowmap(p, sg, pmap + p.off_map[3], lane, true);
-    if (omask & 1u) build_colmap(p, sg, pmap + p.off_map[0], lane, false);
-    if (omask & 2u) build_colmap(p, sg, pmap + p.off_map[1], lane, true);
+    if (omask & 4u) build_rowmap(g, p, sg, pmap + g.off_map(2), lane, false);
+    if (omask & 8u) build_rowmap(g, p, sg, pmap + g.off_map(3), lane, true);
+    if (omask & 1u) build_colmap(g, p, sg, pmap + g.off_map(0), lane, false);
+    if (omask & 2u) build_colmap(g, p, sg, pmap + g.off_map(1), lane, true);
     __syncwarp();
     if (top) {                                                // any cell code | 7 == 7: one atomic OR per map, no RMW race
-        const int nm = p.LPn + c0, nmr = p.LPn + p.W - 1 - c0, nt = p.LPn + r0, ntr = p.LPn + p.H - 1 - r0;
-        if (omask & 4u) atomicOr(reinterpret_cast<unsigned*>(pmap + p.off_map[2] + (r0 + p.V) * p.pitchM + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
-        if (omask & 8u) atomicOr(reinterpret_cast<unsigned*>(pmap + p.off_map[3] + (r0 + p.V) * p.pitchM + ((nmr >> 3) << 2)), 7u << (4 * (nmr & 7)));
-        if (omask & 1u) atomicOr(reinterpret_cast<unsigned*>(pmap + p.off_map[0] + (c0 + p.V) * p.pitchT + ((nt >> 3) << 2)), 7u << (4 * (nt & 7)));
-        if (omask & 2u) atomicOr(reinterpret_cast<unsigned*>(pmap + p.off_map[1] + (c0 + p.V) * p.pitchT + ((ntr >> 3) << 2)), 7u << (4 * (ntr & 7)));
+        const int nm = g.LPn() + c0, nmr = g.LPn() + g.W() - 1 - c0, nt = g.LPn() + r0, ntr = g.LPn() + g.H() - 1 - r0;
+        if (omask & 4u) atomicOr(reinterpret_cast<unsigned*>(pmap + g.off_map(2) + (r0 + g.V()) * g.pitchM() + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
+        if (omask & 8u) atomicOr(reinterpret_cast<unsigned*>(pmap + g.off_map(3) + (r0 + g.V()) * g.pitchM() + ((nmr >> 3) << 2)), 7u << (4 * (nmr & 7)));
+        if (omask & 1u) atomicOr(reinterpret_cast<unsigned*>(pmap + g.off_map(0) + (c0 + g.V()) * g.pitchT() + ((nt >> 3) << 2)), 7u << (4 * (nt & 7)));
+        if (omask & 2u) atomicOr(reinterpret_cast<unsigned*>(pmap + g.off_map(1) + (c0 + g.V()) * g.pitchT() + ((ntr >> 3) << 2)), 7u << (4 * (ntr & 7)));
     }
     __syncwarp();
 
-    uint8_t* gobs = p.obs + (size_t)env * p.ES;
-    if (p.RP == 32) gather_rows<4>(p, pmap, gobs, lane, abase_sh, astep);
-    else if (p.RP == 16) gather_rows<2>(p, pmap, gobs, lane, abase_sh, astep);
-    else gather_rows<0>(p, pmap, gobs, lane, abase_sh, astep);
-    const int tail = p.AS - 3 * p.PS;                         // pad bytes per agent block (0 for the shipped views)
+    uint8_t* gobs = p.obs + (size_t)env * (p.n * g.AS());
+    if (g.RP() == 32) gather_rows<4>(g, p, pmap, gobs, lane, abase_sh, astep);
+    else if (g.RP() == 16) gather_rows<2>(g, p, pmap, gobs, lane, abase_sh, astep);
+    else gather_rows<0>(g, p, pmap, gobs, lane, abase_sh, astep);
+    const int tail = g.AS() - 3 * g.PS();                         // pad bytes per agent block (0 for the shipped views)
     if (tail) for (int i = lane; i < p.n * (tail >> 2); i += 32)
-        *reinterpret_cast<uint32_t*>(gobs + (i / (tail >> 2)) * p.AS + 3 * p.PS + 4 * (i % (tail >> 2))) = 0u;
+        *reinterpret_cast<uint32_t*>(gobs + (i / (tail >> 2)) * g.AS() + 3 * g.PS() + 4 * (i % (tail >> 2))) = 0u;
     if (!p.agents_uniform) {
         // full-colour scheme: every visible agent is re-painted with its own colour (after the row stores)
         __syncwarp();
@@ -556,22 +649,23 @@ __device__ __forceinline__ void render(const KParams& p, const uint8_t* sg, uint
             const uint32_t api = __shfl_sync(kFull, apack, al), apj = __shfl_sync(kFull, apack, j);
             const bool topj = __shfl_sync(kFull, (int)top, j);
             if (!valid || !topj) continue;
-            const int a = (int)(apj & 1023) - (int)(api & 1023) + p.V, b = (int)((apj >> 10) & 1023) - (int)((api >> 10) & 1023) + p.V;
-            if (a < 0 || a >= p.N || b < 0 || b >= p.N) continue;
+            const int a = (int)(apj & 1023) - (int)(api & 1023) + g.V(), b = (int)((apj >> 10) & 1023) - (int)((api >> 10) & 1023) + g.V();
+            if (a < 0 || a >= g.N() || b < 0 || b >= g.N()) continue;
             const int o = api >> 20;
             int y, x;
-            if (o == 2) { y = a; x = b; } else if (o == 0) { x = a; y = p.N - 1 - b; }
-            else if (o == 3) { y = p.N - 1 - a; x = p.N - 1 - b; } else { x = p.N - 1 - a; y = b; }
+            if (o == 2) { y = a; x = b; } else if (o == 0) { x = a; y = g.N() - 1 - b; }
+            else if (o == 3) { y = g.N() - 1 - a; x = g.N() - 1 - b; } else { x = g.N() - 1 - a; y = b; }
             const uint32_t rgb = lut_s[agent_colour_index(j)];
-            uint8_t* d = gobs + al * p.AS + y * p.RP + x;
-            d[0] = (uint8_t)rgb; d[p.PS] = (uint8_t)(rgb >> 8); d[2 * p.PS] = (uint8_t)(rgb >> 16);
+            uint8_t* d = gobs + al * g.AS() + y * g.RP() + x;
+            d[0] = (uint8_t)rgb; d[g.PS()] = (uint8_t)(rgb >> 8); d[2 * g.PS()] = (uint8_t)(rgb >> 16);
         }
     }
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE>
+template <int MODE, class GEO>
 __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_constant__ KParams p) {
+    const GEO g(p);
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t lut_s[16];
     if (threadIdx.x < 16) lut_s[threadIdx.x] = p.lut[threadIdx.x];
@@ -581,8 +675,8 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
     if (env >= p.B) return;
     if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
 
-    uint8_t* sg = smem + (size_t)warp * p.smem_per_warp;
-    uint8_t* pmap = sg + p.off_pmap;
+    uint8_t* sg = smem + (size_t)warp * (g.GS() + g.PMS());
+    uint8_t* pmap = sg + g.GS();
     const bool is_agent = lane < p.n;
     const uint32_t gid = p.gid_base + (uint32_t)env;
     // every global load of the step is issued up front; the map pre-fill below overlaps their latency
@@ -595,25 +689,25 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
         a_rec = p.agent[(size_t)env * p.NA + lane];
         ep_ret = p.ep_ret[(size_t)env * p.NA + lane];
     }
-    const int n16 = p.GS >> 4;
+    const int n16 = g.GS() >> 4;
     uint4 g0 = make_uint4(0, 0, 0, 0);
     {
         const uint4* src = MODE == MODE_RESET ? reinterpret_cast<const uint4*>(p.map->base_grid)
-                                              : reinterpret_cast<const uint4*>(p.grid + (size_t)env * p.GS);
+                                              : reinterpret_cast<const uint4*>(p.grid + (size_t)env * g.GS());
         if (lane < n16) g0 = src[lane];
-        if (p.obs) fill_outside(p, pmap, lane);
+        if (p.obs) fill_outside(g, p, pmap, lane);
         if (lane < n16) reinterpret_cast<uint4*>(sg)[lane] = g0;
         for (int i = lane + 32; i < n16; i += 32) reinterpret_cast<uint4*>(sg)[i] = src[i];
     }
     if (MODE != MODE_RESET && is_agent) {
-        pos = (int)(a_rec & 0xff) * p.W + (int)((a_rec >> 8) & 0xff);
+        pos = (int)(a_rec & 0xff) * g.W() + (int)((a_rec >> 8) & 0xff);
         ori = (int)((a_rec >> 16) & 3);
     }
     __syncwarp();
 
     if (MODE == MODE_STEP) {
         int reward = 0, clean_num = 0;
-        update_moves(p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
+        update_moves(g, p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
         // consume in index order: the lowest index on a cell eats the apple (253-256); mark occupancy
         const unsigned same = __match_any_sync(kFull, pos);
         const int here = is_agent ? sg[pos] : 0;
@@ -623,8 +717,8 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
             else sg[pos] = (uint8_t)(kOcc | here);
         }
         __syncwarp();
-        beams(p, sg, lane, is_agent, act, pos, ori, reward, clean_num);                     // 259-260
-        spawn(p, sg, lane, env, gid, tick);                                                 // 263
+        beams(g, p, sg, lane, is_agent, act, pos, ori, reward, clean_num);                     // 259-260
+        spawn(g, p, sg, lane, env, gid, tick);                                                 // 263
         const int t = t_prev + 1;
         if (is_agent) {
             p.reward[(size_t)env * p.n + lane] = (int8_t)reward;
@@ -644,7 +738,7 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
         for (int i = 0; i < p.n; ++i) {
             uint32_t key = 0;
             if (p.random_spawn && is_sp)
-                key = p.d_spawnkey ? p.d_spawnkey[((size_t)env * p.n + i) * p.G + mycell]
+                key = p.d_spawnkey ? p.d_spawnkey[((size_t)env * p.n + i) * g.G() + mycell]
                                    : philox_word(p, gid, tick, 3u, (uint32_t)(i * p.n_spawn + lane));
             const bool cand = is_sp && !taken;
             const uint32_t mk = __reduce_max_sync(kFull, cand ? key : 0u);
@@ -660,7 +754,7 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
         }
         if (is_agent) sg[pos] |= kOcc;                         // distinct spawn points: no two lanes share a cell
         __syncwarp();
-        spawn(p, sg, lane, env, gid, tick);                                                 // custom_map_update (313)
+        spawn(g, p, sg, lane, env, gid, tick);                                                 // custom_map_update (313)
         ep_ret = 0;
         if (lane == 0) { p.t[env] = 0; p.tick[env] = tick + 1; }
     }
@@ -669,9 +763,9 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
         const unsigned same = __match_any_sync(kFull, pos);
         if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
         __syncwarp();
-        uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * p.GS);
+        uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * g.GS());
         int apples = 0;
-        warp_for(p.GS >> 4, lane, [&](int i) {
+        warp_for(g.GS() >> 4, lane, [&](int i) {
             const uint4 v = reinterpret_cast<const uint4*>(sg)[i];
             dst[i] = v;
             if (MODE == MODE_STEP) apples += count_eq16(v, 0x02020202u);
@@ -682,12 +776,12 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
             if (lane == 0) p.apple_cnt[env] = (uint16_t)apples;
         }
         if (is_agent) {
-            const int r = (int)(((uint32_t)pos * p.invW20) >> 20);
-            p.agent[(size_t)env * p.NA + lane] = (uint32_t)r | ((uint32_t)(pos - r * p.W) << 8) | ((uint32_t)ori << 16);
+            const int r = g.divW(pos);
+            p.agent[(size_t)env * p.NA + lane] = (uint32_t)r | ((uint32_t)(pos - r * g.W()) << 8) | ((uint32_t)ori << 16);
             p.ep_ret[(size_t)env * p.NA + lane] = ep_ret;
         }
     }
-    if (p.obs || p.state_rgb) render(p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
+    if (p.obs || p.state_rgb) render(g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
 }
 
 // ------------------------------------------------------------------ incentive bookkeeping (homophily_learner.py:98-115)
@@ -737,6 +831,7 @@ struct ssd_handle {
     int device;
     size_t smem_bytes;
     int64_t launches;
+    int force_generic;                                        // SSD_B200_GENERIC=1: always use the runtime-geometry kernels
 };
 
 static int fill_common(const ssd_handle* h, const ssd_state* st, const ssd_draws* d, KParams& k) {
@@ -751,18 +846,31 @@ static int fill_common(const ssd_handle* h, const ssd_state* st, const ssd_draws
     return SSD_OK;
 }
 
-template <int MODE>
-static int launch(ssd_handle* h, const KParams& k, void* stream) {
+template <int MODE, class GEO>
+static int launch_geo(ssd_handle* h, const KParams& k, void* stream) {
     static size_t max_smem = 0;                               // the attribute is a per-function maximum: only raise it
     if (h->smem_bytes > max_smem) {
-        SSD_CUDA(cudaFuncSetAttribute(ssd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        SSD_CUDA(cudaFuncSetAttribute(ssd_kernel<MODE, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         max_smem = h->smem_bytes;
     }
     const int grid = (k.B + kWarps - 1) / kWarps;
-    ssd_kernel<MODE><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
+    ssd_kernel<MODE, GEO><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
     ++h->launches;
     SSD_CUDA(cudaGetLastError());
     return SSD_OK;
+}
+
+// The reference's shipped geometries (constants.py maps x yaml view sizes) get compile-time index arithmetic.
+template <int MODE>
+static int launch(ssd_handle* h, const KParams& k, void* stream) {
+    if (!h->force_generic) {
+        if (k.kind == SSD_KIND_HARVEST && k.H == 9 && k.W == 38 && k.V == 15) return launch_geo<MODE, GeoS<SSD_KIND_HARVEST, 9, 38, 15>>(h, k, stream);
+        if (k.kind == SSD_KIND_HARVEST && k.H == 9 && k.W == 38 && k.V == 7) return launch_geo<MODE, GeoS<SSD_KIND_HARVEST, 9, 38, 7>>(h, k, stream);
+        if (k.kind == SSD_KIND_CLEANUP && k.H == 25 && k.W == 18 && k.V == 7) return launch_geo<MODE, GeoS<SSD_KIND_CLEANUP, 25, 18, 7>>(h, k, stream);
+        if (k.kind == SSD_KIND_CLEANUP && k.H == 48 && k.W == 18 && k.V == 7) return launch_geo<MODE, GeoS<SSD_KIND_CLEANUP, 48, 18, 7>>(h, k, stream);
+        if (k.kind == SSD_KIND_CLEANUP && k.H == 10 && k.W == 10 && k.V == 7) return launch_geo<MODE, GeoS<SSD_KIND_CLEANUP, 10, 10, 7>>(h, k, stream);
+    }
+    return launch_geo<MODE, GeoD>(h, k, stream);
 }
 
 extern "C" {
@@ -835,21 +943,13 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     if (!h) { delete hm; return SSD_ERR_INVALID; }
     memset(h, 0, sizeof(*h));
     KParams& k = h->kp;
-    k.kind = cfg->kind; k.B = cfg->n_envs; k.n = n; k.H = H; k.W = W; k.G = G; k.V = V; k.N = 2 * V + 1; k.NN = k.N * k.N;
-    k.GS = round_up(G, 16); k.NA = round_up(n, 4);
-    k.RP = round_up(k.N, 4); k.PS = k.N * k.RP; k.AS = round_up(3 * k.PS, 16); k.ES = n * k.AS;
-    // nibble-packed padded maps; word pitch kept odd so that lanes gathering consecutive rows hit distinct banks
-    k.LPn = round_up(V, 8); k.nw8M = (W + 7) / 8; k.nw8T = (H + 7) / 8;
-    k.maskM8 = (W & 7) ? (1u << (4 * (W & 7))) - 1u : 0xffffffffu;
-    k.maskT8 = (H & 7) ? (1u << (4 * (H & 7))) - 1u : 0xffffffffu;
-    {
-        int wm = (k.LPn + W + V + 7) / 8; if (wm < k.LPn / 8 + k.nw8M) wm = k.LPn / 8 + k.nw8M; if ((wm & 1) == 0) ++wm;
-        int wt = (k.LPn + H + V + 7) / 8; if (wt < k.LPn / 8 + k.nw8T) wt = k.LPn / 8 + k.nw8T; if ((wt & 1) == 0) ++wt;
-        k.pitchM = 4 * wm; k.pitchT = 4 * wt;
-        const int szM = round_up((H + 2 * V) * k.pitchM, 16) + 16, szT = round_up((W + 2 * V) * k.pitchT, 16) + 16;
-        k.off_map[0] = 0; k.off_map[1] = szT; k.off_map[2] = 2 * szT; k.off_map[3] = 2 * szT + szM;
-        k.PMS = 2 * szT + 2 * szM + 16;
-    }
+    const GeoVals gv = make_geo(cfg->kind, H, W, V);
+    k.kind = cfg->kind; k.B = cfg->n_envs; k.n = n; k.H = H; k.W = W; k.G = G; k.V = V; k.N = gv.N; k.NN = gv.NN;
+    k.GS = gv.GS; k.NA = round_up(n, 4);
+    k.RP = gv.RP; k.PS = gv.PS; k.AS = gv.AS; k.ES = n * k.AS;
+    k.LPn = gv.LPn; k.nw8M = gv.nw8M; k.nw8T = gv.nw8T; k.maskM8 = gv.maskM8; k.maskT8 = gv.maskT8;
+    k.pitchM = gv.pitchM; k.pitchT = gv.pitchT; k.PMS = gv.PMS;
+    k.off_map[0] = gv.off0; k.off_map[1] = gv.off1; k.off_map[2] = gv.off2; k.off_map[3] = gv.off3;
     k.episode_limit = cfg->episode_limit; k.fire_cost = cfg->fire_cost; k.hit_penalty = cfg->hit_penalty;
     k.beam_len = cfg->beam_len; k.n_actions = cfg->kind == SSD_KIND_CLEANUP ? 9 : 8;
     k.n_apple = na; k.n_waste = nw; k.n_spawn = ns; k.n_apple4 = (na + 3) / 4; k.n_waste2 = (nw + 1) / 2;
@@ -873,6 +973,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     k.off_pmap = k.GS;
     k.smem_per_warp = k.off_pmap + k.PMS;
     h->smem_bytes = (size_t)kWarps * k.smem_per_warp;
+    { const char* e = getenv("SSD_B200_GENERIC"); h->force_generic = e && e[0] == '1'; }
     h->device = cfg->device;
 
     cudaError_t e = cudaSetDevice(cfg->device);
