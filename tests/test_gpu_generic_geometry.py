@@ -1,0 +1,95 @@
+"""GPU suite: geometries outside the compile-time specialisations -- custom ASCII maps, odd view sizes (generic row
+pitch, non-zero agent-block tail), up to 16 agents, tiny and near-maximum maps -- against the oracle, Philox mode."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def random_map(rs, kind, H, W, n_spawn):
+    """Wall-enclosed random map in the reference alphabet with at least n_spawn 'P' cells."""
+    g = np.full((H, W), " ", dtype="<U1")
+    g[0, :] = g[-1, :] = "@"
+    g[:, 0] = g[:, -1] = "@"
+    inner = [(r, c) for r in range(1, H - 1) for c in range(1, W - 1)]
+    rs.shuffle(inner)
+    it = iter(inner)
+    for _ in range(n_spawn):
+        r, c = next(it)
+        g[r, c] = "P"
+    alphabet = ("B", "H", "R", "S", "@", " ", " ") if kind == "cleanup" else ("A", "A", "@", " ", " ", " ")
+    for r, c in it:
+        g[r, c] = alphabet[rs.randint(len(alphabet))]
+    return ["".join(row) for row in g]
+
+
+CASES = [  # kind, H, W, n_agents, view
+    ("cleanup", 5, 5, 2, 1), ("cleanup", 7, 9, 3, 2), ("cleanup", 12, 11, 16, 3), ("cleanup", 20, 33, 7, 5),
+    ("cleanup", 40, 50, 10, 9), ("harvest", 6, 6, 4, 4), ("harvest", 9, 38, 5, 6), ("harvest", 16, 16, 16, 11),
+    ("harvest", 31, 66, 8, 20), ("cleanup", 45, 45, 12, 31),
+]
+
+
+@pytest.mark.parametrize("kind,H,W,n,view", CASES)
+def test_generic_geometry_matches_oracle(kind, H, W, n, view):
+    from homophily_marl_b200 import mapspec
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    rs = np.random.RandomState(H * 1000 + W * 10 + n)
+    rows = random_map(rs, kind, H, W, n_spawn=min(32, n + 3))
+    if kind == "cleanup":
+        params = mapspec.EnvParams(mapspec.KIND_CLEANUP, "custom", 0.7, 0.1, 0.4, 0.25)
+    else:
+        params = mapspec.EnvParams(mapspec.KIND_HARVEST, "custom", spawn_prob=(0.01, 0.1, 0.2, 0.4))
+    B, T = 24, 30
+    color = "full" if (H + W) % 2 else "simplified"
+    env = SSDBatchEnv(kind, B, n, view_size=view, episode_limit=11, rows=rows, params=params, seed=42, env_gid_base=7,
+                      extra_args=dict(random_spawn_point=True, random_spawn_rotation=None, obs_color=color), want_state=True)
+    lay = env.layout
+    assert lay.obs_row_stride == (2 * view + 4) // 4 * 4 and lay.obs_agent_stride % 16 == 0
+    ora = O.OracleBatch.from_spec(env.spec, n_envs=B, seed=42, env_gid0=7, random_spawn_point=True, spawn_rotation=None)
+    env.reset()
+    ora.reset()
+    assert np.array_equal(env.obs_view().cpu().numpy(), np.stack([ora.obs_one(b) for b in range(B)]))
+    for t in range(T):
+        act = rs.randint(0, env.n_actions, size=(B, n)).astype(np.uint8)
+        env.step(torch.as_tensor(act, device=env.device), want_state=True)
+        out = ora.step(act)
+        for k in ("reward", "clean", "done"):
+            assert np.array_equal(getattr(env, k).cpu().numpy(), out[k]), (t, k)
+        assert np.array_equal(env.apple_cnt.cpu().numpy().view(np.uint16), out["apple_cnt"]), t
+        assert np.array_equal(env.grid.cpu().numpy(), ora.grid), t
+        assert np.array_equal(env.agent_pos.cpu().numpy(), ora.pos_rc), t
+        assert np.array_equal(env.obs_view().cpu().numpy(), out["obs"]), t
+        assert np.array_equal(env.state_rgb.cpu().numpy(), np.stack([ora.state_one(b) for b in range(B)])), t
+        if out["done"].all():
+            env.reset()
+            ora.reset()
+    # pad bytes (row padding and agent-block tail) are zero
+    flat = env.obs_buf.view(B, n, lay.obs_agent_stride).cpu().numpy()
+    planes = flat[:, :, : 3 * lay.obs_plane_stride].reshape(B, n, 3, env.N, lay.obs_row_stride)
+    assert (planes[..., env.N:] == 0).all() and (flat[:, :, 3 * lay.obs_plane_stride:] == 0).all()
+    assert int(ora.envs["error"].sum()) == 0
+
+
+def test_maximum_map_size_and_rejects():
+    from homophily_marl_b200 import _capi
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    rs = np.random.RandomState(1)
+    rows = random_map(rs, "harvest", 32, 64, 8)                      # 2048 cells = SSD_MAX_CELLS
+    env = SSDBatchEnv("harvest", 4, 8, view_size=7, episode_limit=5, rows=rows, seed=1,
+                      params=__import__("homophily_marl_b200").mapspec.EnvParams(1, "custom", spawn_prob=(0, .1, .2, .3)))
+    ora = O.OracleBatch.from_spec(env.spec, n_envs=4, seed=1)
+    env.reset()
+    ora.reset()
+    for t in range(5):
+        act = rs.randint(0, 8, size=(4, 8)).astype(np.uint8)
+        env.step(torch.as_tensor(act, device=env.device))
+        assert np.array_equal(env.obs_view().cpu().numpy(), ora.step(act)["obs"])
+    with pytest.raises(ValueError):
+        SSDBatchEnv("harvest", 4, 2, view_size=7, rows=random_map(rs, "harvest", 33, 64, 4))     # > SSD_MAX_CELLS
+    with pytest.raises(_capi.SsdError) as ei:
+        SSDBatchEnv("harvest", 4, 2, view_size=7, rows=["@@@@", "@PP ", "@@@@"])                  # open border
+    assert ei.value.code == _capi.SSD_ERR_MAP
