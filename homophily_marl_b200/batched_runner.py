@@ -1,0 +1,168 @@
+"""Batched episode runner: B env instances in lockstep, device-resident episode data.
+
+Mirrors ``EpisodeRunner`` of the reference (src/runners/episode_runner.py:8-152) -- same ``setup`` / ``run`` /
+``reset`` / ``get_env_info`` / ``close_env`` / ``save_replay`` surface, same order of ``batch.update`` calls, same
+keys -- but drives ``SSDBatchEnv`` with ``batch_size_run = B`` and hands **device tensors** to
+``EpisodeBatch.update`` (its tensor fast path, src/components/episode_buffer.py:103-104), so no observation ever
+visits the host.  ``new_batch`` is the reference's own ``partial(EpisodeBatch, scheme, groups, B, T+1, ...)``;
+``mac`` is the reference's ``HomophilyMAC`` (or anything with the same three methods).
+
+Differences that follow from B > 1 (all envs share ``episode_limit`` and terminate together, ``get_done`` is
+constantly False in the reference, agent.py:192,243):
+  * ``t_env`` advances by ``B * t`` per call (total env steps), ``n_episodes`` by B;
+  * ``collective_return`` / ``equality_metric`` are summed over the B envs into the stats dict exactly as B
+    successive single-env episodes would.
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+import torch
+
+from . import mapspec
+from .batch_env import SSDBatchEnv
+
+
+class BatchedEpisodeRunner:
+    def __init__(self, args, logger):
+        self.args = args
+        self.logger = logger
+        self.batch_size = self.args.batch_size_run
+        env_args = dict(self.args.env_args)
+        env_args.pop("render", None)
+        env_args.pop("is_replay", None)
+        device = getattr(self.args, "device", "cuda:0")
+        self.env = SSDBatchEnv(self.args.env, self.batch_size, env_args.pop("num_agents"),
+                               map=env_args.pop("map", "default"), view_size=env_args.pop("view_size", 7),
+                               episode_limit=env_args.pop("episode_limit", 100), extra_args=env_args.pop("extra_args", None),
+                               seed=env_args.pop("seed", 0) or 0, device=device if str(device).startswith("cuda") else "cuda:0",
+                               env_gid_base=getattr(self.args, "env_gid_base", 0), want_state=True)
+        self.episode_limit = self.env.episode_limit
+        self.t = 0
+        self.t_env = 0
+        self.train_returns, self.test_returns = [], []
+        self.train_stats, self.test_stats = {}, {}
+        self.log_train_stats_t = -1000000
+        e = self.env
+        avail = [1] * e.n_actions                             # map_env.py:972-980
+        if e.extra_args["disable_rotation_action"]:
+            avail[5] = avail[6] = 0
+        if e.extra_args["disable_fire_action"]:
+            avail[7] = 0
+        self._avail = torch.tensor(avail, dtype=torch.int32, device=e.device).expand(e.B, e.n, e.n_actions).contiguous()
+        self._orient_vec = torch.as_tensor(mapspec.ORIENT_VEC, dtype=torch.float32, device=e.device)
+
+    # ---- reference surface ------------------------------------------------------------------------------
+    def setup(self, scheme, groups, preprocess, mac, batch_cls=None):
+        """As episode_runner.py:28-31.  ``batch_cls`` defaults to the reference's EpisodeBatch when it is importable."""
+        if batch_cls is None:
+            from components.episode_buffer import EpisodeBatch as batch_cls   # the reference package (src/ on sys.path)
+        self.new_batch = partial(batch_cls, scheme, groups, self.batch_size, self.episode_limit + 1,
+                                 preprocess=preprocess, device=self.args.device)
+        self.mac = mac
+
+    def use_batch_factory(self, new_batch):
+        """``new_batch()`` must return a fresh reference ``EpisodeBatch`` for B episodes of T+1 steps."""
+        self.new_batch = new_batch
+
+    def get_env_info(self):
+        e = self.env
+        return {"state_shape": (3, e.H, e.W), "obs_shape": (3, e.N, e.N), "n_actions": e.n_actions, "n_agents": e.n,
+                "episode_limit": self.episode_limit, "units_type_id": None, "own_feature_size": None,
+                "state_dims": (e.H, e.W), "obs_dims": (e.N, e.N)}
+
+    def save_replay(self):
+        return None
+
+    def close_env(self):
+        self.env.close()
+
+    def reset(self):
+        self.batch = self.new_batch()
+        self.env.reset()
+        self.t = 0
+
+    # ---- device-side views of what the reference env returns per step -------------------------------------
+    def _pre_transition(self):
+        e = self.env
+        e.render(want_obs=False, want_state=True)             # get_state(); obs are already rendered by step/reset
+        return {"state": e.state_rgb.float() / 256, "avail_actions": self._avail,
+                "obs": e.obs_view().float() / 256, "agent_pos": e.agent_pos.float(),
+                "agent_orientation": self._orient_vec[e.agent_orient.long()]}
+
+    def run(self, test_mode=False):
+        self.reset()
+        e, B = self.env, self.batch_size
+        terminated = False
+        episode_return = torch.zeros(B, e.n, device=e.device)
+        self.mac.init_hidden(batch_size=B)
+        if getattr(self.args, "mac", None) == "separate_mac":
+            self.mac.init_latent(batch_size=B)
+        homophily = "homophily" in getattr(self.args, "name", "homophily")
+        env_info = {}
+        while not terminated:
+            self.batch.update(self._pre_transition(), ts=self.t)
+            if homophily:
+                actions = self.mac.select_actions_env(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
+            else:
+                actions = self.mac.select_actions(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
+            actions_env = actions % self.args.n_actions
+            e.step(actions_env.reshape(B, e.n).to(device=e.device, dtype=torch.uint8).contiguous())
+            reward = e.reward.float()
+            episode_return += reward
+            terminated = bool(e.done[0].item())               # the one host sync per step: all envs end together
+            post = {"actions": actions, "reward": reward if getattr(self.args, "ind_reward", True) else reward.sum(1, keepdim=True),
+                    "terminated": e.done.view(B, 1), "clean_num": e.clean.float(),
+                    "apple_den": (e.apple_cnt.to(torch.int32) & 0xFFFF).double().view(B, 1).expand(B, e.n) / e.G}
+            self.batch.update(post, ts=self.t)
+            if homophily:
+                actions_inc = self.mac.select_actions_inc(actions, self.batch, t_ep=self.t, t_env=self.t_env,
+                                                          test_mode=test_mode, agent_pos_replay=e.agent_pos.float())
+                self.batch.update({"actions_inc": actions_inc}, ts=self.t)
+            self.t += 1
+        self.batch.update(self._pre_transition(), ts=self.t)
+        if homophily:
+            actions = self.mac.select_actions_env(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
+            actions_inc = self.mac.select_actions_inc(actions, self.batch, t_ep=self.t, t_env=self.t_env,
+                                                      test_mode=test_mode, agent_pos_replay=e.agent_pos.float())
+            self.batch.update({"actions_inc": actions_inc}, ts=self.t)
+        else:
+            actions = self.mac.select_actions(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
+        self.batch.update({"actions": actions}, ts=self.t)
+
+        # termination info of every env (map_env.py:897-912), accumulated like B single-env episodes
+        R = e.ep_ret.double().cpu().numpy()
+        coll = R.sum(axis=1)
+        denom = 2 * e.n * np.abs(R).sum(axis=1)
+        pair = np.abs(R[:, None, :] - R[:, :, None]).sum(axis=(1, 2))
+        eq = np.where(coll != 0, 1 - pair / np.where(denom == 0, 1, denom), 1.0)
+        env_info = {"collective_return": float(coll.sum()), "equality_metric": float(eq.sum())}
+        self.last_env_info = {"collective_return": coll, "equality_metric": eq}
+
+        cur_stats = self.test_stats if test_mode else self.train_stats
+        cur_returns = self.test_returns if test_mode else self.train_returns
+        log_prefix = "test_" if test_mode else ""
+        cur_stats.update({k: cur_stats.get(k, 0) + env_info.get(k, 0) for k in set(cur_stats) | set(env_info)})
+        cur_stats["n_episodes"] = B + cur_stats.get("n_episodes", 0)
+        cur_stats["ep_length"] = self.t * B + cur_stats.get("ep_length", 0)
+        if not test_mode:
+            self.t_env += self.t * B
+        cur_returns.extend(episode_return.cpu().numpy())
+        if test_mode and (len(self.test_returns) >= getattr(self.args, "test_nepisode", 1)):
+            self._log(cur_returns, cur_stats, log_prefix)
+        elif self.t_env - self.log_train_stats_t >= getattr(self.args, "runner_log_interval", 10000):
+            self._log(cur_returns, cur_stats, log_prefix)
+            if hasattr(getattr(self.mac, "action_selector", None), "epsilon"):
+                self.logger.log_stat("epsilon", self.mac.action_selector.epsilon, self.t_env)
+            self.log_train_stats_t = self.t_env
+        return self.batch
+
+    def _log(self, returns, stats, prefix):
+        self.logger.log_stat(prefix + "return_mean", np.mean(returns), self.t_env)
+        self.logger.log_stat(prefix + "return_std", np.std(returns), self.t_env)
+        returns.clear()
+        for k, v in stats.items():
+            if k not in {"n_episodes", "clean_num", "apple_den", "agent_pos", "agent_orientation"}:
+                self.logger.log_stat(prefix + k + "_mean", v / stats["n_episodes"], self.t_env)
+        stats.clear()

@@ -83,14 +83,15 @@ class _SSDEnv(MultiAgentEnv):
     ENV_NAME = None
 
     def __init__(self, ascii_map=None, num_agents=1, render=False, seed=None, episode_limit=100,
-                 is_replay=False, view_size=7, map="default", extra_args=None, device=None, quiet=False):
+                 is_replay=False, view_size=7, map="default", extra_args=None, device=None, quiet=False,
+                 env_gid_base=0):
         extra = dict(random_spawn_point=False, random_spawn_rotation=0, disable_rotation_action=True,
                      disable_fire_action=True, obs_color="simplified")
         extra.update(extra_args or {})
         device = device or os.environ.get("SSD_B200_DEVICE", "cuda:0")
         self.sim = SSDBatchEnv(self.ENV_NAME, 1, num_agents, map=map, view_size=view_size,
                                episode_limit=episode_limit, extra_args=extra, seed=0 if seed is None else int(seed),
-                               device=device, rows=ascii_map, want_state=True)
+                               device=device, rows=ascii_map, want_state=True, env_gid_base=env_gid_base)
         if not quiet:                                   # cleanup.py:56-58 / harvest.py:24-26
             print("map difficulty: {}".format(map))
             for row in self.sim.spec.rows:
@@ -107,7 +108,8 @@ class _SSDEnv(MultiAgentEnv):
         self.clean_num = np.zeros(num_agents)
         self.apple_den = np.zeros(num_agents)
         self._actions_dev = torch.zeros((1, num_agents), dtype=torch.uint8, device=self.sim.device)
-        self.sim.reset()                                # valid state before the first reset()
+        self.sim.reset()                                # valid state before the first reset() ...
+        self.sim.tick_buf.zero_()                       # ... which then replays the same draws (tick 0)
 
     # ------------------------------------------------------------------ step / reset
     def step(self, actions):

@@ -52,3 +52,37 @@ def test_seeded_anchor_hashes_of_the_reference():
     assert hA.hexdigest()[:16] == "bd7111014f50657d" and hB.hexdigest()[:16] == "a45f7cb95a093744"
     assert env.rewards.tolist() == [-93.0, -114.0, -116.0, -86.0, -100.0]
     assert info["equality_metric"] == 0.9363457760314342
+
+
+def test_fakebatch_has_the_update_semantics_of_the_reference_episodebatch():
+    """tests/test_batched_runner.py checks the batched runner through a stand-in EpisodeBatch; this pins the stand-in
+    against the reference's EpisodeBatch.update (src/components/episode_buffer.py:87-116) on the CPU."""
+    import numpy as np
+    import torch
+    refshim._import_registry()
+    from components.episode_buffer import EpisodeBatch
+    from test_batched_runner import FakeBatch, _scheme
+    n, A, H, W, N, B, T = 3, 9, 10, 10, 15, 2, 4
+    fs = _scheme(n, A, H, W, N)
+    scheme = {"state": {"vshape": (3, H, W)}, "obs": {"vshape": (3, N, N), "group": "agents"},
+              "actions": {"vshape": (1,), "group": "agents", "dtype": torch.long},
+              "avail_actions": {"vshape": (A,), "group": "agents", "dtype": torch.int}, "reward": {"vshape": (n,)},
+              "terminated": {"vshape": (1,), "dtype": torch.uint8}, "clean_num": {"vshape": (n,)}, "apple_den": {"vshape": (n,)},
+              "agent_pos": {"vshape": (n, 2)}, "agent_orientation": {"vshape": (n, 2)},
+              "actions_inc": {"vshape": (n, 1), "group": "agents", "dtype": torch.long}}
+    ref = EpisodeBatch(scheme, {"agents": n}, B, T, device="cpu")
+    fake = FakeBatch(fs, B, T, "cpu")
+    rs = np.random.RandomState(0)
+    for t in range(T):
+        data = {"state": torch.from_numpy(rs.randint(0, 256, (B, 3, H, W)).astype(np.uint8)).float() / 256,
+                "obs": torch.from_numpy(rs.randint(0, 256, (B, n, 3, N, N)).astype(np.uint8)).float() / 256,
+                "avail_actions": torch.ones(B, n, A, dtype=torch.int32), "agent_pos": torch.rand(B, n, 2),
+                "agent_orientation": torch.rand(B, n, 2), "actions": torch.randint(0, A, (B, n, 1)),
+                "reward": torch.randint(-1, 2, (B, n)).float(), "terminated": torch.zeros(B, 1, dtype=torch.uint8),
+                "clean_num": torch.rand(B, n), "apple_den": torch.rand(B, n, dtype=torch.float64),
+                "actions_inc": torch.randint(0, 3, (B, n, n, 1))}
+        ref.update(data, ts=t)
+        fake.update(data, ts=t)
+    for k in fs:
+        assert torch.equal(ref[k], fake[k]) and ref[k].dtype == fake[k].dtype, k
+    assert torch.equal(ref["filled"], fake["filled"])
