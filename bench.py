@@ -33,6 +33,8 @@ WORKLOADS = {
     "cleanup10_b2048": ("cleanup", "default10", 10, 7, 2048, "configs[2] Cleanup default10, 16384 envs over 8 GPUs"),
     "cleanup3_b4096": ("cleanup", "default3", 3, 7, 4096, "configs[3] map/agents at B=4096"),
     "harvest5_b65536": ("harvest", "default5", 5, 15, 65536, "configs[4] Harvest default5, 65536 envs obs stress"),
+    "cleanup5_b65536": ("cleanup", "default5", 5, 7, 65536, "configs[0] map/agents at B=65536 (large-batch regime)"),
+    "cleanup10_b16384": ("cleanup", "default10", 10, 7, 16384, "configs[2] whole 16384-env job on ONE GPU"),
 }
 L2_BYTES = 126 * 2 ** 20
 METRIC = "agent-steps/sec (step+obs, device-timed)"
