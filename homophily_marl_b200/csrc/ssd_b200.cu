@@ -88,8 +88,8 @@ __host__ __device__ constexpr GeoVals make_geo(int kind, int H, int W, int V) {
     int wt = (g.LPn + H + V + 7) / 8; if (wt < g.LPn / 8 + g.nw8T) wt = g.LPn / 8 + g.nw8T; if ((wt & 1) == 0) ++wt;
     g.pitchM = 4 * wm; g.pitchT = 4 * wt;
     const int szM = cround_up((H + 2 * V) * g.pitchM, 16) + 16, szT = cround_up((W + 2 * V) * g.pitchT, 16) + 16;
-    g.off0 = 0; g.off1 = szT; g.off2 = 2 * szT; g.off3 = 2 * szT + szM;     // index = orientation: MT, MTR, M, MR
-    g.PMS = 2 * szT + 2 * szM + 16;
+    g.off0 = 16; g.off1 = 16; g.off2 = 16 + szT; g.off3 = 16 + szT;        // by orientation: LEFT/RIGHT -> MT, UP/DOWN -> M
+    g.PMS = szT + szM + 32;
     return g;
 }
 
@@ -435,22 +435,28 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 
 // Row gather from NIBBLE-PACKED padded index maps.
-// Four zero-padded copies of the map live in shared memory as 4-bit colour indices (8 cells per word):
-//   M   [padded row][col]      MR  [padded row][W-1-col]      MT  [padded col][row]      MTR [padded col][H-1-row]
+// Two zero-padded copies of the map live in shared memory as 4-bit colour indices (8 cells per word):
+//   M [padded row][col]   and   MT [padded col][row]
 // so that for every orientation an output row of the rotated egocentric window (np.rot90 k=1,3,0,2 for
-// LEFT, RIGHT, UP, DOWN; map_env.py:806-813) is ONE ascending run of N nibbles:
-//   UP    out[y][:] = M  [r-V+y][c-V ...]      DOWN  out[y][:] = MR [r+V-y][(W-1-c)-V ...]
-//   LEFT  out[y][:] = MT [c+V-y][r-V ...]      RIGHT out[y][:] = MTR[c-V+y][(H-1-r)-V ...]
-// A lane owns one (agent, y) output row: it loads the <=5 words holding the run, funnel-shifts them to
-// pixel 0 (SHF), and every 16 bits of the result ARE the PRMT selector that looks 4 pixels up in the
-// 8-entry colour LUT held in two registers per plane.  The finished row leaves the SM as one 32-byte
-// (st.global.v8.b32 -> STG.E.ENL2.256) or 16-byte store per plane.  Indices: 0-5 cell codes, 6 outside, 7 agent.
+// LEFT, RIGHT, UP, DOWN; map_env.py:806-813) is ONE run of N nibbles:
+//   UP    out[y][x] = M [r-V+y][c-V+x]  ascending       DOWN  out[y][x] = M [r+V-y][c+V-x]  descending
+//   LEFT  out[y][x] = MT[c+V-y][r-V+x]  ascending       RIGHT out[y][x] = MT[c-V+y][r+V-x]  descending
+// A lane owns one (agent, y) output row: it loads the <=5 words holding the run (nibble-reversing them for a
+// descending run: one PRMT byte swap + one shift/merge), funnel-shifts them to pixel 0 (SHF), and every 16 bits
+// of the result ARE the PRMT selector that looks 4 pixels up in the 8-entry colour LUT held in two registers
+// per plane.  The finished row leaves the SM as one 32-byte (st.global.v8.b32 -> STG.E.ENL2.256) or 16-byte
+// store per plane.  Indices: 0-5 cell codes, 6 outside, 7 agent.
+__device__ __forceinline__ uint32_t nibble_reverse(uint32_t x) {
+    const uint32_t y = prmt(x, 0u, 0x0123);
+    return ((y << 4) & 0xf0f0f0f0u) | ((y >> 4) & 0x0f0f0f0fu);
+}
+
 template <int OCT_T>
 struct RowUnit {                                              // one (agent, y) output row in flight
     uint32_t L[OCT_T > 0 ? OCT_T + 1 : 1];
     const uint32_t* w;
     uint8_t* dst;
-    uint32_t sh;
+    uint32_t sh, rev;
     bool valid;
 };
 
@@ -464,11 +470,17 @@ __device__ __forceinline__ void fetch_row(const GEO& g, const KParams& p, const 
     const uint32_t ab = __shfl_sync(kFull, abase_sh, al);
     const int as = __shfl_sync(kFull, astep, al);
     U.w = reinterpret_cast<const uint32_t*>(pmap + (ab & 0xffffu) + (U.valid ? y * as : 0));
-    U.sh = ab >> 16;
+    U.sh = (ab >> 16) & 31u;
+    U.rev = (ab >> 24) & 1u;
     U.dst = gobs + al * g.AS() + y * g.RP();
     if constexpr (OCT_T > 0) {
+        if (U.rev) {                                          // descending run: words walk down, nibbles are reversed
 #pragma unroll
-        for (int k = 0; k <= OCT_T; ++k) U.L[k] = U.w[k];     // always in bounds: invalid lanes read agent 0's row 0
+            for (int k = 0; k <= OCT_T; ++k) U.L[k] = nibble_reverse(*(U.w - k));
+        } else {
+#pragma unroll
+            for (int k = 0; k <= OCT_T; ++k) U.L[k] = U.w[k]; // always in bounds: invalid lanes read agent 0's row 0
+        }
     }
 }
 
@@ -492,9 +504,9 @@ __device__ __forceinline__ void emit_row(const GEO& g, const KParams& p, const R
         }
     } else {
         const int WR = g.RP() >> 2, OCT = (WR + 1) >> 1;
-        uint32_t prev = U.w[0];
+        uint32_t prev = U.rev ? nibble_reverse(U.w[0]) : U.w[0];
         for (int k = 0; k < OCT; ++k) {
-            const uint32_t cur = U.w[k + 1];
+            const uint32_t cur = U.rev ? nibble_reverse(*(U.w - (k + 1))) : U.w[k + 1];
             uint32_t v = __funnelshift_r(prev, cur, sh);
             prev = cur;
             for (int hlf = 0; hlf < 2; ++hlf, v >>= 16) {
@@ -526,42 +538,32 @@ __device__ __forceinline__ void gather_rows(const GEO& g, const KParams& p, cons
 
 // Nibble-packed padded maps, built one aligned 32-bit word (8 cells) at a time.  Map cells start at nibble
 // LPn (V rounded up to 8) of a padded row, so only the last word of a row needs its tail set to "outside".
-// Source contiguous along the run (M, and MR when `mirror`).
 template <class GEO>
-__device__ __forceinline__ void build_rowmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane, bool mirror) {
+__device__ __forceinline__ void build_rowmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
     const uint32_t* sgw = reinterpret_cast<const uint32_t*>(sg);
     const int total = g.H() * g.nw8M();
+#pragma unroll 2
     for (int i = lane; i < total; i += 32) {
         const int r = g.divMW(i), j = i - r * g.nw8M();
-        uint32_t x0, x1;
-        if (!mirror) {
-            const int sb = r * g.W() + 8 * j, wi = sb >> 2;
-            const uint32_t sel = 0x3210u + 0x1111u * (sb & 3);
-            const uint32_t a0 = sgw[wi], a1 = sgw[wi + 1], a2 = sgw[wi + 2];
-            x0 = prmt(a0, a1, sel); x1 = prmt(a1, a2, sel);
-        } else {
-            const int sb = r * g.W() + g.W() - 1 - 8 * j, wi = sb >> 2;          // highest source byte first
-            const uint32_t sel = (uint32_t)((0x0123701267015670ull >> (16 * (sb & 3))) & 0xffffu);
-            const uint32_t a0 = sgw[wi], a1 = sgw[max(wi - 1, 0)], a2 = sgw[max(wi - 2, 0)];
-            x0 = prmt(a0, a1, sel); x1 = prmt(a1, a2, sel);
-        }
+        const int sb = r * g.W() + 8 * j, wi = sb >> 2;       // first source byte of this word (grid row r, col 8j)
+        const uint32_t sel = 0x3210u + 0x1111u * (sb & 3);
+        const uint32_t a0 = sgw[wi], a1 = sgw[wi + 1], a2 = sgw[wi + 2];
+        const uint32_t x0 = prmt(a0, a1, sel), x1 = prmt(a1, a2, sel);
         uint32_t w = prmt(x0 | (x0 >> 4), x1 | (x1 >> 4), 0x6420);            // 8 bytes -> 8 nibbles
         if (j == g.nw8M() - 1) w = (w & g.maskM8()) | (0x66666666u & ~g.maskM8());
         *reinterpret_cast<uint32_t*>(map + (r + g.V()) * g.pitchM() + (g.LPn() >> 1) + 4 * j) = w;
     }
 }
-// Source strided by W (MT, and MTR when `mirror`).
+// Transposed map: source strided by W.
 template <class GEO>
-__device__ __forceinline__ void build_colmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane, bool mirror) {
+__device__ __forceinline__ void build_colmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
     const int total = g.W() * g.nw8T();
+#pragma unroll 2
     for (int i = lane; i < total; i += 32) {
         const int c = g.divMTW(i), j = i - c * g.nw8T();
         uint32_t b[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {                          // rows past the map are clamped, then masked below
-            const int rr = mirror ? max(g.H() - 1 - (8 * j + k), 0) : min(8 * j + k, g.H() - 1);
-            b[k] = sg[rr * g.W() + c];
-        }
+        for (int k = 0; k < 8; ++k) b[k] = sg[min(8 * j + k, g.H() - 1) * g.W() + c];   // rows past the map: clamped, masked below
         const uint32_t y0 = b[0] | (b[1] << 4), y1 = b[2] | (b[3] << 4), y2 = b[4] | (b[5] << 4), y3 = b[6] | (b[7] << 4);
         uint32_t w = prmt(prmt(y0, y1, 0x0040), prmt(y2, y3, 0x0040), 0x5410);
         if (j == g.nw8T() - 1) w = (w & g.maskT8()) | (0x66666666u & ~g.maskT8());
@@ -603,30 +605,27 @@ __device__ __forceinline__ void render(const GEO& g, const KParams& p, const uin
     if (!p.obs) return;
 
     // the maps were pre-filled with "outside the map" at kernel start (fill_outside); now the cells, then the agents
-    // per agent: which map, first word of its window row 0, row step, funnel shift   (o: 0 LEFT 1 RIGHT 2 UP 3 DOWN)
-    const bool colmap = ori < 2, mirror = (ori == 1) || (ori == 3);
+    // per agent: which map, first word of its window row 0, row step, funnel shift, direction   (o: 0 LEFT 1 RIGHT 2 UP 3 DOWN)
+    const bool colmap = ori < 2, rev = (ori == 1) || (ori == 3);
     const int rowc = colmap ? c0 : r0;                        // coordinate that selects the map row
-    const int runc = colmap ? (mirror ? g.H() - 1 - r0 : r0) : (mirror ? g.W() - 1 - c0 : c0);   // coordinate along the run
+    const int runc = colmap ? r0 : c0;                        // coordinate along the run
     const int pitch = colmap ? g.pitchT() : g.pitchM();
     const bool down = (ori == 0) || (ori == 3);               // window row y walks towards smaller map rows
-    const int s = g.LPn() + runc - g.V();
+    const int s = g.LPn() + runc + (rev ? g.V() : -g.V());    // first pixel of the run (highest nibble when descending)
     const uint32_t abase_sh = (uint32_t)(g.off_map(ori) + (rowc + (down ? 2 * g.V() : 0)) * pitch + ((s >> 3) << 2))
-                              | ((uint32_t)((s & 7) * 4) << 16);
+                              | ((uint32_t)((rev ? 7 - (s & 7) : (s & 7)) * 4) << 16) | ((uint32_t)rev << 24);
     const int astep = down ? -pitch : pitch;
-    const unsigned omask = (__ballot_sync(kFull, is_agent && ori == 0) ? 1u : 0u) | (__ballot_sync(kFull, is_agent && ori == 1) ? 2u : 0u) |
-                           (__ballot_sync(kFull, is_agent && ori == 2) ? 4u : 0u) | (__ballot_sync(kFull, is_agent && ori == 3) ? 8u : 0u);
+    const bool needT = __ballot_sync(kFull, is_agent && ori < 2) != 0, needM = __ballot_sync(kFull, is_agent && ori >= 2) != 0;
     __syncwarp();
-    if (omask & 4u) build_rowmap(g, p, sg, pmap + g.off_map(2), lane, false);
-    if (omask & 8u) build_rowmap(g, p, sg, pmap + g.off_map(3), lane, true);
-    if (omask & 1u) build_colmap(g, p, sg, pmap + g.off_map(0), lane, false);
-    if (omask & 2u) build_colmap(g, p, sg, pmap + g.off_map(1), lane, true);
+    uint8_t* MT = pmap + g.off_map(0);
+    uint8_t* M = pmap + g.off_map(2);
+    if (needM) build_rowmap(g, p, sg, M, lane);
+    if (needT) build_colmap(g, p, sg, MT, lane);
     __syncwarp();
     if (top) {                                                // any cell code | 7 == 7: one atomic OR per map, no RMW race
-        const int nm = g.LPn() + c0, nmr = g.LPn() + g.W() - 1 - c0, nt = g.LPn() + r0, ntr = g.LPn() + g.H() - 1 - r0;
-        if (omask & 4u) atomicOr(reinterpret_cast<unsigned*>(pmap + g.off_map(2) + (r0 + g.V()) * g.pitchM() + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
-        if (omask & 8u) atomicOr(reinterpret_cast<unsigned*>(pmap + g.off_map(3) + (r0 + g.V()) * g.pitchM() + ((nmr >> 3) << 2)), 7u << (4 * (nmr & 7)));
-        if (omask & 1u) atomicOr(reinterpret_cast<unsigned*>(pmap + g.off_map(0) + (c0 + g.V()) * g.pitchT() + ((nt >> 3) << 2)), 7u << (4 * (nt & 7)));
-        if (omask & 2u) atomicOr(reinterpret_cast<unsigned*>(pmap + g.off_map(1) + (c0 + g.V()) * g.pitchT() + ((ntr >> 3) << 2)), 7u << (4 * (ntr & 7)));
+        const int nm = g.LPn() + c0, nt = g.LPn() + r0;
+        if (needM) atomicOr(reinterpret_cast<unsigned*>(M + (r0 + g.V()) * g.pitchM() + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
+        if (needT) atomicOr(reinterpret_cast<unsigned*>(MT + (c0 + g.V()) * g.pitchT() + ((nt >> 3) << 2)), 7u << (4 * (nt & 7)));
     }
     __syncwarp();
 
