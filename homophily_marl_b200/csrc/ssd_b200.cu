@@ -342,17 +342,24 @@ __device__ __forceinline__ void beams(const GEO& g, const KParams& p, uint8_t* s
 
 // ------------------------------------------------------------------ spawning (cleanup.py:165-204, harvest.py:92-122)
 template <class GEO>
-__device__ __forceinline__ void spawn(const GEO& g, const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick) {
+__device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick) {
     const MapDev* __restrict__ m = p.map;
     uint32_t tA = 1, tW = 0;
-    if (g.kind() == SSD_KIND_CLEANUP) {
-        int h = 0;                                            // compute_permitted_area: count 'H' (occupancy bit ignored)
-        warp_for(g.GS() >> 4, lane, [&](int i) {
-            uint4 v = reinterpret_cast<const uint4*>(sg)[i];
+    // one pass over the staged grid: apples (density numerator, map_env.py:291-292; none lies under an agent after
+    // consume) in the high half, Cleanup's waste count (compute_permitted_area, occupancy bit ignored) in the low half
+    int acc = 0;
+    warp_for(g.GS() >> 4, lane, [&](int i) {
+        uint4 v = reinterpret_cast<const uint4*>(sg)[i];
+        acc += count_eq16(v, 0x02020202u) << 16;
+        if (g.kind() == SSD_KIND_CLEANUP) {
             v.x &= 0x7f7f7f7fu; v.y &= 0x7f7f7f7fu; v.z &= 0x7f7f7f7fu; v.w &= 0x7f7f7f7fu;
-            h += count_eq16(v, 0x03030303u);
-        });
-        h = __reduce_add_sync(kFull, h);
+            acc += count_eq16(v, 0x03030303u);
+        }
+    });
+    acc = __reduce_add_sync(kFull, acc);
+    int apples = acc >> 16;
+    if (g.kind() == SSD_KIND_CLEANUP) {
+        const int h = acc & 0xffff;
         tA = __ldg(&m->thr_apple[h]);
         tW = __ldg(&m->thr_waste[h]);
     }
@@ -420,6 +427,8 @@ __device__ __forceinline__ void spawn(const GEO& g, const KParams& p, uint8_t* s
     }
     if (wcell >= 0 && lane == 0) sg[wcell] = (uint8_t)(SSD_CELL_WASTE | (sg[wcell] & kOcc));
     __syncwarp();
+    if (__ballot_sync(kFull, decided != 0)) apples += __reduce_add_sync(kFull, __popcll(decided));
+    return apples;
 }
 
 // ------------------------------------------------------------------ render (map_env.py:360-379, 418-446, 795-815, 923-957)
@@ -717,7 +726,7 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
         }
         __syncwarp();
         beams(g, p, sg, lane, is_agent, act, pos, ori, reward, clean_num);                     // 259-260
-        spawn(g, p, sg, lane, env, gid, tick);                                                 // 263
+        const int apples = spawn(g, p, sg, lane, env, gid, tick);                              // 263, 291-292
         const int t = t_prev + 1;
         if (is_agent) {
             p.reward[(size_t)env * p.n + lane] = (int8_t)reward;
@@ -725,6 +734,7 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
             ep_ret += reward;                                                               // 885-888
         }
         if (lane == 0) {
+            p.apple_cnt[env] = (uint16_t)apples;
             p.done[env] = t >= p.episode_limit;                                             // 890-894
             p.t[env] = t;
             p.tick[env] = tick + 1;
@@ -763,17 +773,7 @@ __global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_consta
         if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
         __syncwarp();
         uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * g.GS());
-        int apples = 0;
-        warp_for(g.GS() >> 4, lane, [&](int i) {
-            const uint4 v = reinterpret_cast<const uint4*>(sg)[i];
-            dst[i] = v;
-            if (MODE == MODE_STEP) apples += count_eq16(v, 0x02020202u);
-        });
-        if (MODE == MODE_STEP) {
-            // apple density numerator (map_env.py:291-292): after consume + spawn no apple lies under an agent
-            apples = __reduce_add_sync(kFull, apples);
-            if (lane == 0) p.apple_cnt[env] = (uint16_t)apples;
-        }
+        warp_for(g.GS() >> 4, lane, [&](int i) { dst[i] = reinterpret_cast<const uint4*>(sg)[i]; });
         if (is_agent) {
             const int r = g.divW(pos);
             p.agent[(size_t)env * p.NA + lane] = (uint32_t)r | ((uint32_t)(pos - r * g.W()) << 8) | ((uint32_t)ori << 16);
