@@ -7,9 +7,10 @@
 //   * lanes are spawn candidates during apple/waste spawning (4 apple points or 2 waste
 //     points per Philox4x32-10 call);
 //   * lanes are output pixel ROWS during the egocentric render: a row of the rotated window is one
-//     contiguous run in a zero-padded (or transposed) index map held in shared memory, so a lane
-//     realigns it with PRMT, colours 4 pixels per PRMT through an 8-entry register LUT and writes the
-//     finished row with one 256-bit (st.global.v8.b32, SASS STG.E.ENL2.256) or 128-bit store per plane.
+//     run of N nibbles in a zero-padded nibble-packed index map (or its transpose) held in shared memory,
+//     so a lane funnel-shifts it to pixel 0, colours 4 pixels per PRMT through an 8-entry register LUT
+//     and writes the finished row with one 256-bit (st.global.v8.b32, SASS STG.E.ENL2.256) or 128-bit
+//     store per plane.
 // The env's grid is staged in shared memory for the whole step.  No tensor cores: nothing here is a
 // contraction.  HBM traffic per env-step is the algorithmic 2G + n(3N^2+11)+3 bytes (+ row padding),
 // ~98% of it observation WRITES.
@@ -43,9 +44,9 @@ struct MapDev {
 };
 
 struct KParams {
-    int kind, B, n, H, W, G, V, N, NN;
+    int kind, B, n, H, W, G, V, N;
     int GS, NA, RP, PS, AS, ES;               // strides (ssd_layout)
-    int pitchM, pitchT, off_map[4], PMS;      // nibble maps (index = orientation: MT, MTR, M, MR): row pitches, byte offsets, total bytes
+    int pitchM, pitchT, off_map[4], PMS;      // nibble maps M / MT: row pitches, byte offset by orientation (0,1 -> MT; 2,3 -> M), total bytes
     int LPn, nw8M, nw8T;                      // left pad in nibbles (V rounded up to 8), words per map row holding cells
     uint32_t maskM8, maskT8;                  // valid-nibble mask of the last word of a map row
     int agents_uniform;                       // all agent colours equal -> no per-agent repaint
@@ -72,14 +73,14 @@ struct KParams {
 // (ssd_create) and, for the reference's shipped maps, at compile time by the kernels (GeoS), so that index
 // arithmetic folds into immediates; any other geometry runs the same code on runtime values (GeoD).
 struct GeoVals {
-    int kind, H, W, V, G, GS, N, NN, RP, PS, AS, LPn, nw8M, nw8T, pitchM, pitchT, off0, off1, off2, off3, PMS;
+    int kind, H, W, V, G, GS, N, RP, PS, AS, LPn, nw8M, nw8T, pitchM, pitchT, off0, off1, off2, off3, PMS;
     uint32_t maskM8, maskT8;
 };
 __host__ __device__ constexpr int cround_up(int v, int m) { return (v + m - 1) / m * m; }
 __host__ __device__ constexpr GeoVals make_geo(int kind, int H, int W, int V) {
     GeoVals g{};
     g.kind = kind; g.H = H; g.W = W; g.V = V; g.G = H * W; g.GS = cround_up(H * W, 16);
-    g.N = 2 * V + 1; g.NN = g.N * g.N; g.RP = cround_up(g.N, 4); g.PS = g.N * g.RP; g.AS = cround_up(3 * g.PS, 16);
+    g.N = 2 * V + 1; g.RP = cround_up(g.N, 4); g.PS = g.N * g.RP; g.AS = cround_up(3 * g.PS, 16);
     // nibble-packed padded maps; word pitch kept odd so that lanes gathering consecutive rows hit distinct banks
     g.LPn = cround_up(V, 8); g.nw8M = (W + 7) / 8; g.nw8T = (H + 7) / 8;
     g.maskM8 = (W & 7) ? (1u << (4 * (W & 7))) - 1u : 0xffffffffu;
@@ -104,7 +105,6 @@ struct GeoS {                                                 // compile-time ge
     __device__ __forceinline__ int G() const { return v.G; }
     __device__ __forceinline__ int GS() const { return v.GS; }
     __device__ __forceinline__ int N() const { return v.N; }
-    __device__ __forceinline__ int NN() const { return v.NN; }
     __device__ __forceinline__ int RP() const { return v.RP; }
     __device__ __forceinline__ int PS() const { return v.PS; }
     __device__ __forceinline__ int AS() const { return v.AS; }
@@ -133,7 +133,6 @@ struct GeoD {                                                 // runtime geometr
     __device__ __forceinline__ int G() const { return p.G; }
     __device__ __forceinline__ int GS() const { return p.GS; }
     __device__ __forceinline__ int N() const { return p.N; }
-    __device__ __forceinline__ int NN() const { return p.NN; }
     __device__ __forceinline__ int RP() const { return p.RP; }
     __device__ __forceinline__ int PS() const { return p.PS; }
     __device__ __forceinline__ int AS() const { return p.AS; }
@@ -943,7 +942,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     memset(h, 0, sizeof(*h));
     KParams& k = h->kp;
     const GeoVals gv = make_geo(cfg->kind, H, W, V);
-    k.kind = cfg->kind; k.B = cfg->n_envs; k.n = n; k.H = H; k.W = W; k.G = G; k.V = V; k.N = gv.N; k.NN = gv.NN;
+    k.kind = cfg->kind; k.B = cfg->n_envs; k.n = n; k.H = H; k.W = W; k.G = G; k.V = V; k.N = gv.N;
     k.GS = gv.GS; k.NA = round_up(n, 4);
     k.RP = gv.RP; k.PS = gv.PS; k.AS = gv.AS; k.ES = n * k.AS;
     k.LPn = gv.LPn; k.nw8M = gv.nw8M; k.nw8T = gv.nw8T; k.maskM8 = gv.maskM8; k.maskT8 = gv.maskT8;
