@@ -33,10 +33,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in (SRC, HDR))
 
 
-def build(force: bool = False, extra_flags=(), verbose: bool = False) -> str:
-    if not force and not needs_build():
+LIB_CHECK = os.path.join(PKG_DIR, "libssd_b200_check.so")
+
+
+def build_checked(force: bool = False) -> str:
+    """Variant with -DSSD_BOUNDS_CHECK (own shared-memory index checks; see ssd_debug_oob_count)."""
+    if not force and os.path.exists(LIB_CHECK) and os.path.getmtime(LIB_CHECK) >= max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        return LIB_CHECK
+    return build(force=True, extra_flags=["-DSSD_BOUNDS_CHECK"], out=LIB_CHECK)
+
+
+def build(force: bool = False, extra_flags=(), verbose: bool = False, out: str = LIB) -> str:
+    if not force and out == LIB and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", LIB, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", out, SRC]
     env = dict(os.environ)
     if os.path.exists("/usr/bin/gcc"):
         cmd += ["-ccbin", "/usr/bin/g++"]
@@ -46,7 +56,7 @@ def build(force: bool = False, extra_flags=(), verbose: bool = False) -> str:
         print(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stderr[-4000:])
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

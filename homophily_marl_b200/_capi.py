@@ -9,14 +9,14 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libssd_b200.so")
+LIB_PATH = os.path.join(PKG_DIR, "libssd_b200_check.so" if os.environ.get("SSD_B200_CHECKED") == "1" else "libssd_b200.so")
 
 SSD_OK, SSD_ERR_INVALID, SSD_ERR_CUDA, SSD_ERR_SPAWN, SSD_ERR_MAP = 0, -1, -2, -3, -4
 
 # every symbol include/ssd_b200.h declares (checked by tests/test_capi_symbols.py against the header text)
 EXPORTS = ("ssd_abi_version", "ssd_error_string", "ssd_last_cuda_error", "ssd_prob_to_threshold",
            "ssd_create", "ssd_destroy", "ssd_get_layout", "ssd_reset", "ssd_step", "ssd_render",
-           "ssd_step_host", "ssd_incentive", "ssd_launch_count")
+           "ssd_step_host", "ssd_incentive", "ssd_launch_count", "ssd_debug_oob_count")
 
 
 class SsdConfig(C.Structure):
@@ -84,6 +84,7 @@ def load():
                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ssd_launch_count.restype = C.c_int64
     L.ssd_launch_count.argtypes = [C.c_void_p]
+    L.ssd_debug_oob_count.restype = C.c_int64
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

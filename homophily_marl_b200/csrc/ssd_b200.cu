@@ -33,6 +33,15 @@ constexpr uint16_t kNoPoint = 0xFFFF;
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
 
+// -DSSD_BOUNDS_CHECK builds the checked variant (libssd_b200_check.so): every data-dependent shared-memory index is
+// tested against its tile and violations are counted (compute-sanitizer is closed on the GPU pool).
+#ifdef SSD_BOUNDS_CHECK
+__device__ unsigned long long g_oob_count = 0;
+#define SSD_CHECK(cond) do { if (!(cond)) atomicAdd(&g_oob_count, 1ull); } while (0)
+#else
+#define SSD_CHECK(cond) do { } while (0)
+#endif
+
 // Static per-map tables, resident in global memory (read through the L1 read-only path).
 struct MapDev {
     uint8_t  base_grid[SSD_MAX_CELLS];        // reset grid in cell codes
@@ -217,6 +226,7 @@ __device__ __forceinline__ void update_moves(const GEO& g, const KParams& p, con
         const int f = 2 * (ori * 4 + act);
         const int dr = (int)((kDr >> f) & 3u) - 1, dc = (int)((kDc >> f) & 3u) - 1;
         const int q = pos + dr * g.W() + dc;
+        SSD_CHECK(q >= 0 && q < g.G());
         prop = sg[q] == SSD_CELL_WALL ? pos : q;             // agent.py:111-119
     }
     unsigned in_moves = __ballot_sync(kFull, mover);
@@ -312,6 +322,7 @@ __device__ __forceinline__ void beams(const GEO& g, const KParams& p, uint8_t* s
         if (lane < 3) {                                       // the three parallel rays (728-730)
             int q = posi + (lane == 0 ? d : (lane == 1 ? rs : -rs));
             for (int k = 0; k < p.beam_len; ++k) {            // maps are wall-enclosed: a ray cannot leave the map
+                SSD_CHECK(q >= 0 && q < g.G());
                 const int v = sg[q], code = v & 0x7f;
                 if (code == SSD_CELL_WALL) break;             // 737
                 if (v & kOcc) {                               // agents absorb beams (741-749)
@@ -380,6 +391,8 @@ __device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg
                 uint32_t thr = tA;
                 if (g.kind() == SSD_KIND_HARVEST) {
                     int cnt = 0;                                               // j^2+k^2 <= 2: the 3x3 block (harvest.py:107-116)
+#pragma unroll
+                    SSD_CHECK(c - g.W() - 1 >= 0 && c + g.W() + 1 < g.G());
 #pragma unroll
                     for (int a = -1; a <= 1; ++a)
 #pragma unroll
@@ -481,6 +494,11 @@ __device__ __forceinline__ void fetch_row(const GEO& g, const KParams& p, const 
     U.sh = (ab >> 16) & 31u;
     U.rev = (ab >> 24) & 1u;
     U.dst = gobs + al * g.AS() + y * g.RP();
+    {   // the <= OCT+1 words of the run, ascending or descending, must lie inside this warp's map tile
+        const int nwords = (OCT_T > 0 ? OCT_T : ((g.RP() >> 2) + 1) >> 1) + 1;
+        const long off = reinterpret_cast<const uint8_t*>(U.w) - pmap;
+        SSD_CHECK(off >= (U.rev ? 4L * (nwords - 1) : 0L) && off + (U.rev ? 4L : 4L * nwords) <= g.PMS());
+    }
     if constexpr (OCT_T > 0) {
         if (U.rev) {                                          // descending run: words walk down, nibbles are reversed
 #pragma unroll
@@ -555,10 +573,12 @@ __device__ __forceinline__ void build_rowmap(const GEO& g, const KParams& p, con
         const int r = g.divMW(i), j = i - r * g.nw8M();
         const int sb = r * g.W() + 8 * j, wi = sb >> 2;       // first source byte of this word (grid row r, col 8j)
         const uint32_t sel = 0x3210u + 0x1111u * (sb & 3);
+        SSD_CHECK(wi >= 0 && 4 * (wi + 3) <= g.GS() + g.PMS());          // the last words may run into the (ignored) map tile
         const uint32_t a0 = sgw[wi], a1 = sgw[wi + 1], a2 = sgw[wi + 2];
         const uint32_t x0 = prmt(a0, a1, sel), x1 = prmt(a1, a2, sel);
         uint32_t w = prmt(x0 | (x0 >> 4), x1 | (x1 >> 4), 0x6420);            // 8 bytes -> 8 nibbles
         if (j == g.nw8M() - 1) w = (w & g.maskM8()) | (0x66666666u & ~g.maskM8());
+        SSD_CHECK((r + g.V()) * g.pitchM() + (g.LPn() >> 1) + 4 * j + 4 <= (g.H() + 2 * g.V()) * g.pitchM());
         *reinterpret_cast<uint32_t*>(map + (r + g.V()) * g.pitchM() + (g.LPn() >> 1) + 4 * j) = w;
     }
 }
@@ -575,6 +595,7 @@ __device__ __forceinline__ void build_colmap(const GEO& g, const KParams& p, con
         const uint32_t y0 = b[0] | (b[1] << 4), y1 = b[2] | (b[3] << 4), y2 = b[4] | (b[5] << 4), y3 = b[6] | (b[7] << 4);
         uint32_t w = prmt(prmt(y0, y1, 0x0040), prmt(y2, y3, 0x0040), 0x5410);
         if (j == g.nw8T() - 1) w = (w & g.maskT8()) | (0x66666666u & ~g.maskT8());
+        SSD_CHECK((c + g.V()) * g.pitchT() + (g.LPn() >> 1) + 4 * j + 4 <= (g.W() + 2 * g.V()) * g.pitchT());
         *reinterpret_cast<uint32_t*>(map + (c + g.V()) * g.pitchT() + (g.LPn() >> 1) + 4 * j) = w;
     }
 }
@@ -1071,5 +1092,15 @@ int ssd_incentive(const int64_t* actions_inc, const float* reward, int64_t rows,
 }
 
 int64_t ssd_launch_count(const ssd_handle* h) { return h ? h->launches : -1; }
+
+int64_t ssd_debug_oob_count(void) {
+#ifdef SSD_BOUNDS_CHECK
+    unsigned long long v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(&v, g_oob_count, sizeof(v)) != cudaSuccess) return -2;
+    return (int64_t)v;
+#else
+    return -1;
+#endif
+}
 
 }  // extern "C"

@@ -161,6 +161,10 @@ int ssd_incentive(const int64_t* actions_inc, const float* reward, int64_t rows,
 /* Kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t ssd_launch_count(const ssd_handle* h);
 
+/* Checked build only (-DSSD_BOUNDS_CHECK, libssd_b200_check.so): number of shared-memory index violations seen so
+ * far on the current device; -1 in the normal build. */
+int64_t ssd_debug_oob_count(void);
+
 #ifdef __cplusplus
 }
 #endif

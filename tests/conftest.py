@@ -19,3 +19,15 @@ def _built_oracle():
     from oracle import oracle
     oracle.build()
     yield
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _checked_build_reports_no_violation():
+    """With SSD_B200_CHECKED=1 the whole GPU suite runs on libssd_b200_check.so; no index violation may be seen."""
+    yield
+    if os.environ.get("SSD_B200_CHECKED") == "1":
+        import torch
+        if torch.cuda.is_available():
+            from homophily_marl_b200 import _capi
+            n = _capi.load().ssd_debug_oob_count()
+            assert n == 0, f"checked build counted {n} shared-memory index violations"

@@ -93,3 +93,18 @@ def test_maximum_map_size_and_rejects():
     with pytest.raises(_capi.SsdError) as ei:
         SSDBatchEnv("harvest", 4, 2, view_size=7, rows=["@@@@", "@PP ", "@@@@"])                  # open border
     assert ei.value.code == _capi.SSD_ERR_MAP
+
+
+def test_checked_build_sees_no_shared_memory_violation():
+    """compute-sanitizer is closed on the GPU pool, so the library has its own checked variant (-DSSD_BOUNDS_CHECK):
+    every data-dependent shared-memory index is tested against its tile.  Runs the all-paths workload in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import runpy, sys; sys.argv=['x']; runpy.run_path(%r, run_name='__main__'); "
+            "from homophily_marl_b200 import _capi; n = _capi.load().ssd_debug_oob_count(); print('OOB', n); assert n == 0, n"
+            % os.path.join(root, "profiles", "sanitizer_case.py"))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, "SSD_B200_CHECKED": "1"},
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OOB 0" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
