@@ -834,6 +834,18 @@ inline int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return SSD_ERR
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// Makes the handle's device current for the duration of a call and restores the caller's device afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = err == cudaSuccess; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 uint32_t magic20(int d, int max_x) {
     // smallest m with floor(x*m / 2^20) == floor(x / d) for all 0 <= x <= max_x (verified exhaustively)
     uint32_t m = (uint32_t)(((1u << 20) + d - 1) / d);
@@ -851,6 +863,7 @@ struct ssd_handle {
     size_t smem_bytes;
     int64_t launches;
     int force_generic;                                        // SSD_B200_GENERIC=1: always use the runtime-geometry kernels
+    bool smem_attr_set[3];                                    // per kernel mode: dynamic shared-memory limit raised on this device
 };
 
 static int fill_common(const ssd_handle* h, const ssd_state* st, const ssd_draws* d, KParams& k) {
@@ -867,10 +880,11 @@ static int fill_common(const ssd_handle* h, const ssd_state* st, const ssd_draws
 
 template <int MODE, class GEO>
 static int launch_geo(ssd_handle* h, const KParams& k, void* stream) {
-    static size_t max_smem = 0;                               // the attribute is a per-function maximum: only raise it
-    if (h->smem_bytes > max_smem) {
+    DeviceGuard guard(h->device);
+    SSD_CUDA(guard.err);
+    if (!h->smem_attr_set[MODE]) {                            // a handle has one geometry, so one instantiation per mode
         SSD_CUDA(cudaFuncSetAttribute(ssd_kernel<MODE, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        max_smem = h->smem_bytes;
+        h->smem_attr_set[MODE] = true;
     }
     const int grid = (k.B + kWarps - 1) / kWarps;
     ssd_kernel<MODE, GEO><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
@@ -995,7 +1009,8 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     { const char* e = getenv("SSD_B200_GENERIC"); h->force_generic = e && e[0] == '1'; }
     h->device = cfg->device;
 
-    cudaError_t e = cudaSetDevice(cfg->device);
+    DeviceGuard guard(cfg->device);
+    cudaError_t e = guard.err;
     if (e == cudaSuccess) e = cudaMalloc(&h->d_map, sizeof(MapDev));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_map, hm, sizeof(MapDev), cudaMemcpyHostToDevice);
     delete hm;
@@ -1011,6 +1026,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
 
 int ssd_destroy(ssd_handle* h) {
     if (!h) return SSD_ERR_INVALID;
+    DeviceGuard guard(h->device);
     cudaFree(h->d_map);
     delete h;
     return SSD_OK;
@@ -1056,6 +1072,8 @@ int ssd_render(ssd_handle* h, const ssd_state* st, uint8_t* obs, uint8_t* state_
 int ssd_step_host(ssd_handle* h, const ssd_state* st, const uint8_t* h_actions, uint8_t* d_actions,
                   const ssd_step_out* d_out, const ssd_step_out* h_out, void* stream) {
     if (!h || !h_actions || !d_actions || !d_out || !h_out) return SSD_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    SSD_CUDA(guard.err);
     const KParams& k = h->kp;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t B = (size_t)k.B;

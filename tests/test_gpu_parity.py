@@ -255,3 +255,27 @@ def test_incentive_bookkeeping_matches_torch():
         ok = ok or (torch.equal(outs[0], want_env) and torch.equal(outs[1], want_inc))
         assert torch.allclose(outs[0], want_env, rtol=0, atol=1e-7) and torch.allclose(outs[1], want_inc, rtol=0, atol=1e-7)
     assert ok, "neither division mode is bit-identical to torch on this device"
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_env_on_second_device_leaves_current_device_alone():
+    """The C ABI makes the handle's device current only for the duration of a call (one process may hold several)."""
+    assert torch.cuda.current_device() == 0
+    env1, ora = _make_pair("cleanup5", 32, 50, seed=8)
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    env2 = SSDBatchEnv("cleanup", 32, 5, map="default5", view_size=7, episode_limit=50, seed=8, device="cuda:1",
+                       extra_args=dict(random_spawn_point=True, random_spawn_rotation=None))
+    assert torch.cuda.current_device() == 0
+    env1.reset()
+    env2.reset()
+    ora.reset()
+    rs = np.random.RandomState(4)
+    for t in range(10):
+        act = rs.randint(0, 9, size=(32, 5)).astype(np.uint8)
+        env1.step(torch.as_tensor(act, device="cuda:0"))
+        env2.step(torch.as_tensor(act, device="cuda:1"))
+        out = ora.step(act)
+        assert torch.cuda.current_device() == 0
+        assert np.array_equal(env1.obs_view().cpu().numpy(), out["obs"])
+        assert np.array_equal(env2.obs_view().cpu().numpy(), out["obs"])
+    env2.close()
