@@ -95,14 +95,20 @@ class ClockSampler:
         except Exception:
             self.h = None
 
+    def sample(self):
+        """One synchronous sample (also called right after the timed work is enqueued, so short runs get one under load)."""
+        if self.h is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            pass
+
     def _run(self):
         while not self._stop.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            except Exception:
-                pass
-            self._stop.wait(0.01)
+            self.sample()
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self.h is not None:
@@ -263,6 +269,7 @@ def run_b200(a):
                 for _ in range(a.steps):
                     one_step()
             ev1.record(stream)
+            clk.sample()                                      # the GPU is still executing the enqueued steps here
             barrier()
         elapsed_ms = ev0.elapsed_time(ev1)
         if use_graph:

@@ -279,3 +279,57 @@ def test_env_on_second_device_leaves_current_device_alone():
         assert np.array_equal(env1.obs_view().cpu().numpy(), out["obs"])
         assert np.array_equal(env2.obs_view().cpu().numpy(), out["obs"])
     env2.close()
+
+
+def test_full_size_harvest_65536_properties_and_sampled_oracle():
+    """BASELINE configs[4]: Harvest default5, 65536 envs x 5 agents.  Size-independent properties on the whole batch
+    (determinism, apple-count checksum, walls never entered, own pixel, padding zero) + the oracle on sampled envs."""
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    B, T = 65536, 12
+    mk = lambda: SSDBatchEnv("harvest", B, 5, map="default5", view_size=15, episode_limit=100, seed=17,  # noqa: E731
+                             extra_args=dict(random_spawn_point=True, random_spawn_rotation=None))
+    env, twin = mk(), mk()
+    sample = list(range(0, B, 4099)) + [B - 1]
+    oras = {b: O.OracleBatch.from_spec(env.spec, n_envs=1, seed=17, env_gid0=b, random_spawn_point=True, spawn_rotation=None)
+            for b in sample}
+    env.reset()
+    twin.reset()
+    for o in oras.values():
+        o.reset()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(T):
+        act = torch.randint(0, 8, (B, 5), generator=g, device="cuda", dtype=torch.int32).to(torch.uint8)
+        env.step(act)
+        twin.step(act)
+        a_host = act[sample].cpu().numpy()
+        obs_s = env.obs_view()[sample].cpu().numpy()
+        rew_s = env.reward[sample].cpu().numpy()
+        for k, b in enumerate(sample):
+            out = oras[b].step(a_host[k:k + 1])
+            assert np.array_equal(obs_s[k], out["obs"][0]) and np.array_equal(rew_s[k], out["reward"][0]), (t, b)
+    assert torch.equal(env.obs_buf, twin.obs_buf) and torch.equal(env.grid_buf, twin.grid_buf)          # deterministic
+    assert torch.equal((env.grid == 2).flatten(1).sum(1).to(torch.int32), env.apple_cnt.to(torch.int32) & 0xFFFF)
+    pos = env.agent_pos.long()
+    cell = env.grid[torch.arange(B, device="cuda")[:, None], pos[..., 0], pos[..., 1]]
+    assert bool((cell != 1).all())
+    assert bool((env.obs_view()[:, :, 2, 15, 15] == 255).all())
+    lay = env.layout
+    rows = env.obs_buf.view(B, 5, 3, 31, lay.obs_row_stride)
+    assert bool((rows[..., 31:] == 0).all())
+    assert len(torch.unique(env.agent_buf[:4096], dim=0)) > 4000                                          # envs really differ
+
+
+def test_full_size_cleanup10_16384_vs_oracle():
+    """BASELINE configs[2] on one GPU: Cleanup default10, 10 agents, 16384 envs, a few steps against the oracle."""
+    B = 16384
+    env, ora = _make_pair("cleanup10", B, 100, seed=23)
+    env.reset()
+    ora.reset(threads=8)
+    rs = np.random.RandomState(6)
+    for t in range(6):
+        act = rs.randint(0, 9, size=(B, 10)).astype(np.uint8)
+        act[:, :4] = 8 if t % 2 else act[:, :4]                    # plenty of CLEAN beams so that spawning switches on
+        env.step(torch.as_tensor(act, device=env.device))
+        out = ora.step(act, threads=8)
+        _assert_out_equal(env, out, f"t={t}")
+    _assert_state_equal(env, ora, "final")
