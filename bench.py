@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--obs-color", default="simplified", choices=["simplified", "full"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--masked-actions", action="store_true",
+                    help="draw actions from the yaml-masked set ({0-4,8} cleanup / {0-4} harvest) instead of all n_actions")
     return ap.parse_args()
 
 
@@ -72,7 +74,8 @@ def workload_config(a, world):
     env, mp, n, view, B, what = WORKLOADS[a.workload]
     B = a.envs or B
     return dict(workload=f"{a.workload}: {what}", env=env, map=mp, num_agents=n, view_size=view, envs_per_gpu=B,
-                global_envs=B * world, episode_limit=100, actions="uniform over all n_actions",
+                global_envs=B * world, episode_limit=100,
+                actions="uniform over the yaml-masked set" if a.masked_actions else "uniform over all n_actions",
                 extra_args="yaml defaults" if not a.random_spawn else "random spawn point+rotation",
                 obs_color=a.obs_color, obs_format="u8 RGB planes, pixel rows padded to a multiple of 4 bytes")
 
@@ -214,6 +217,9 @@ def run_b200(a):
     n_act_slots = 2 * limit
     g = torch.Generator(device=dev).manual_seed(a.seed * 1000 + rank)
     actions = torch.randint(0, env.n_actions, (n_act_slots, B, n), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+    if a.masked_actions:                                       # disable_rotation_action / disable_fire_action (yaml defaults)
+        allowed = torch.tensor([0, 1, 2, 3, 4] + ([8] if env.n_actions == 9 else []), device=dev, dtype=torch.uint8)
+        actions = allowed[torch.randint(0, len(allowed), (n_act_slots, B, n), generator=g, device=dev)]
 
     state = {"t": 0}
 
@@ -336,6 +342,10 @@ def run_b200(a):
             r = time_oracle(cfg, a, steps=20, warmup=3, budget_s=20.0, threads=threads)
             line["cpu_baseline"] = {"value": r["value"], "unit": "agent-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{r['envs']} envs x 20 steps of the same workload (C port of the reference env, step+get_obs)"}
+            r1 = time_oracle(cfg, a, steps=10, warmup=2, budget_s=6.0, threads=1)
+            line["cpu_baseline_1core"] = {"value": r1["value"], "unit": "agent-steps/s", "cores": 1, "kind": "port",
+                                          "sample": f"{r1['envs']} envs x 10 steps; the reference itself is single-env, single-core "
+                                                    "(episode_runner.py:13) and ~50x slower than this C port (BASELINE.md)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -333,3 +333,23 @@ def test_full_size_cleanup10_16384_vs_oracle():
         out = ora.step(act, threads=8)
         _assert_out_equal(env, out, f"t={t}")
     _assert_state_equal(env, ora, "final")
+
+
+def test_single_env_1000_steps_like_baseline_config0():
+    """BASELINE configs[0] shape: Cleanup default5, 5 agents, ONE env, 1000 random-action steps in a single episode."""
+    env, ora = _make_pair("cleanup5", 1, 1000, seed=0, random_spawn=False)
+    env.reset()
+    ora.reset()
+    rs = np.random.RandomState(123)
+    acts = rs.randint(0, 9, size=(1000, 1, 5)).astype(np.uint8)
+    dev_acts = torch.as_tensor(acts, device=env.device)
+    obs_sum = 0
+    for t in range(1000):
+        env.step(dev_acts[t])
+        out = ora.step(acts[t])
+        if t % 50 == 49 or t == 999:
+            _assert_out_equal(env, out, f"t={t}")
+            _assert_state_equal(env, ora, f"t={t}")
+        obs_sum += int(out["obs"].sum())
+    assert bool(env.done[0].item()) and obs_sum > 0
+    assert np.array_equal(env.ep_ret.cpu().numpy(), ora.ep_ret)
