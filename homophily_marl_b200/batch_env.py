@@ -207,22 +207,37 @@ class SSDBatchEnv:
         s = self.state_rgb if want_state else None
         _capi.check(self.lib.ssd_render(self._h, C.byref(self._st), _ptr(o), _ptr(s), self._stream()))
 
-    def make_host_io(self, with_obs=True):
+    def make_host_io(self, with_obs=True, with_state=False):
         """Pinned host mirrors for ``step_host`` (the reference-facing call with host buffers)."""
         pin = lambda t: torch.zeros(t.shape, dtype=t.dtype).pin_memory()  # noqa: E731
         io = dict(actions=torch.zeros((self.B, self.n), dtype=torch.uint8).pin_memory(),
                   reward=pin(self.reward), clean=pin(self.clean), apple_cnt=pin(self.apple_cnt), done=pin(self.done),
-                  obs=pin(self.obs_buf) if with_obs else None)
+                  obs=pin(self.obs_buf) if with_obs else None,
+                  state=pin(self.state_rgb) if (with_state and self.state_rgb is not None) else None,
+                  agent=pin(self.agent_buf))
         io["d_actions"] = torch.zeros((self.B, self.n), dtype=torch.uint8, device=self.device)
         return io
 
     def step_host(self, io):
-        """H2D actions -> step -> D2H reward/clean/apple_cnt/done(/obs) -> stream sync, all inside the C call."""
-        d_out = self._step_out(None, io["obs"] is not None, False)
+        """H2D actions -> step -> D2H reward/clean/apple_cnt/done(/obs/state) -> stream sync, all inside the C call."""
+        want_state = io.get("state") is not None
+        d_out = self._step_out(None, io["obs"] is not None, want_state)
         h_out = _capi.SsdStepOut(io["reward"].data_ptr(), io["clean"].data_ptr(), io["apple_cnt"].data_ptr(),
-                                 io["done"].data_ptr(), io["obs"].data_ptr() if io["obs"] is not None else None, None)
+                                 io["done"].data_ptr(), io["obs"].data_ptr() if io["obs"] is not None else None,
+                                 io["state"].data_ptr() if want_state else None)
         _capi.check(self.lib.ssd_step_host(self._h, C.byref(self._st), _ptr(io["actions"]), _ptr(io["d_actions"]),
                                            C.byref(d_out), C.byref(h_out), self._stream()))
+
+    def pull_host(self, io, obs=True, state=True, agent=True):
+        """Copies the current observation / state image / agent records into the pinned mirrors (one sync)."""
+        if obs and io.get("obs") is not None:
+            io["obs"].copy_(self.obs_buf, non_blocking=True)
+        if state and io.get("state") is not None:
+            self.render(want_obs=False, want_state=True)
+            io["state"].copy_(self.state_rgb, non_blocking=True)
+        if agent:
+            io["agent"].copy_(self.agent_buf, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
 
     @property
     def launch_count(self):

@@ -107,9 +107,13 @@ class _SSDEnv(MultiAgentEnv):
         self.rewards = None
         self.clean_num = np.zeros(num_agents)
         self.apple_den = np.zeros(num_agents)
-        self._actions_dev = torch.zeros((1, num_agents), dtype=torch.uint8, device=self.sim.device)
+        self._io = self.sim.make_host_io(with_obs=True, with_state=True)   # pinned host mirrors: one sync per call
+        lay = self.sim.layout
+        self._obs_host = self._io["obs"].numpy().reshape(-1)[: lay.obs_env_stride]
+        self._obs_strides = (lay.obs_agent_stride, lay.obs_plane_stride, lay.obs_row_stride, 1)
         self.sim.reset()                                # valid state before the first reset() ...
         self.sim.tick_buf.zero_()                       # ... which then replays the same draws (tick 0)
+        self.sim.pull_host(self._io)
 
     # ------------------------------------------------------------------ step / reset
     def step(self, actions):
@@ -118,16 +122,17 @@ class _SSDEnv(MultiAgentEnv):
         for a in acts[:self.num_agents]:
             if not 0 <= a < self.n_actions:
                 raise KeyError(a)                        # agent.py:176,237 action_map lookup
-        self._actions_dev.copy_(torch.tensor([acts[:self.num_agents]], dtype=torch.uint8), non_blocking=False)
-        self.sim.step(self._actions_dev)
-        sim = self.sim
-        reward = sim.reward[0].cpu().numpy().astype(float)
+        io, sim = self._io, self.sim
+        io["actions"][0] = torch.tensor(acts[:self.num_agents], dtype=torch.uint8)
+        sim.step_host(io)                                # H2D actions, fused step+obs+state kernel, D2H results, sync
+        sim.pull_host(io, obs=False, state=False, agent=True)
+        reward = io["reward"][0].numpy().astype(float)
         if self.rewards is None:
             self.rewards = reward
         else:
             self.rewards += reward
         self._episode_steps += 1
-        terminated = bool(sim.done[0].item())            # python bool: SURVEY 8b pitfall
+        terminated = bool(io["done"][0])                 # python bool: SURVEY 8b pitfall
         info = {}
         if terminated:
             collective_return = self.rewards.sum()
@@ -136,8 +141,8 @@ class _SSDEnv(MultiAgentEnv):
                 equality_metric = 1 - (np.abs(self.rewards.reshape(1, -1) - self.rewards.reshape(-1, 1)).sum()) / (
                     2 * len(self.rewards) * np.abs(self.rewards).sum())
             info = {"collective_return": collective_return, "equality_metric": equality_metric}
-        self.clean_num = sim.clean[0].cpu().numpy().astype(float)
-        density = int(sim.apple_cnt[0].item()) / sim.G
+        self.clean_num = io["clean"][0].numpy().astype(float)
+        density = (int(io["apple_cnt"][0]) & 0xFFFF) / sim.G
         self.apple_den = np.full(self.n_agents, density, dtype=float)
         info["clean_num"] = self.clean_num
         info["apple_den"] = self.apple_den
@@ -146,19 +151,25 @@ class _SSDEnv(MultiAgentEnv):
     def reset(self):
         """Reset the environment (map_env.py:986-993); returns None like the reference."""
         self.sim.reset()
+        self.sim.pull_host(self._io)
         self._episode_steps = 0
         self.rewards = None
         return
 
-    # ------------------------------------------------------------------ queries
+    # ------------------------------------------------------------------ queries (served from the pinned mirrors)
+    def _agent_records(self):
+        return self._io["agent"][0, :self.num_agents].numpy().astype(np.int64)
+
     def get_agent_pos(self):
-        return self.sim.agent_pos[0].cpu().numpy().astype(float)
+        a = self._agent_records()
+        return np.stack([a & 0xFF, (a >> 8) & 0xFF], axis=-1).astype(float)
 
     def get_agent_orientation(self):
-        return mapspec.ORIENT_VEC[self.sim.agent_orient[0].cpu().numpy()].astype(float)
+        return mapspec.ORIENT_VEC[(self._agent_records() >> 16) & 3].astype(float)
 
     def _obs_u8(self):
-        return self.sim.obs_view()[0].cpu().numpy()
+        n, N = self.num_agents, self.sim.N
+        return np.lib.stride_tricks.as_strided(self._obs_host, shape=(n, 3, N, N), strides=self._obs_strides)
 
     def get_obs(self):
         """List of n arrays (3, N, N) float = u8 / 256 (map_env.py:923-945)."""
@@ -172,8 +183,7 @@ class _SSDEnv(MultiAgentEnv):
 
     def get_state(self):
         """(3, H, W) float = u8 / 256 (map_env.py:950-957)."""
-        self.sim.render(want_obs=False, want_state=True)
-        return self.sim.state_rgb[0].cpu().numpy() / 256
+        return self._io["state"][0].numpy() / 256
 
     def get_state_size(self):
         return (3, self.sim.H, self.sim.W)
