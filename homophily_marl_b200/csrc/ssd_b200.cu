@@ -27,7 +27,13 @@
 
 namespace {
 
-constexpr int kWarps = 4;                 // env instances per CTA
+#ifndef SSD_WARPS
+#define SSD_WARPS 4
+#endif
+#ifndef SSD_MIN_BLOCKS
+#define SSD_MIN_BLOCKS 8
+#endif
+constexpr int kWarps = SSD_WARPS;         // env instances per CTA
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kNoPoint = 0xFFFF;
 
@@ -692,7 +698,7 @@ __device__ __forceinline__ void render(const GEO& g, const KParams& p, const uin
 
 // ------------------------------------------------------------------ the kernel
 template <int MODE, class GEO>
-__global__ void __launch_bounds__(kWarps * 32, 8) ssd_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const __grid_constant__ KParams p) {
     const GEO g(p);
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t lut_s[16];
