@@ -574,7 +574,7 @@ template <class GEO>
 __device__ __forceinline__ void build_rowmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
     const uint32_t* sgw = reinterpret_cast<const uint32_t*>(sg);
     const int total = g.H() * g.nw8M();
-#pragma unroll 2
+#pragma unroll 4
     for (int i = lane; i < total; i += 32) {
         const int r = g.divMW(i), j = i - r * g.nw8M();
         const int sb = r * g.W() + 8 * j, wi = sb >> 2;       // first source byte of this word (grid row r, col 8j)
@@ -592,7 +592,7 @@ __device__ __forceinline__ void build_rowmap(const GEO& g, const KParams& p, con
 template <class GEO>
 __device__ __forceinline__ void build_colmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
     const int total = g.W() * g.nw8T();
-#pragma unroll 2
+#pragma unroll 4
     for (int i = lane; i < total; i += 32) {
         const int c = g.divMTW(i), j = i - c * g.nw8T();
         uint32_t b[8];
@@ -612,9 +612,8 @@ __device__ __forceinline__ void fill_outside(const GEO& g, const KParams& p, uin
     const uint4 v6 = make_uint4(0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u);
     uint4* q = reinterpret_cast<uint4*>(pmap);
     const int n16 = g.PMS() >> 4;
-    int i = lane;
-    for (; i + 96 < n16; i += 128) { q[i] = v6; q[i + 32] = v6; q[i + 64] = v6; q[i + 96] = v6; }
-    for (; i < n16; i += 32) q[i] = v6;
+#pragma unroll 8
+    for (int i = lane; i < n16; i += 32) q[i] = v6;           // trip count is a compile-time constant for the shipped maps
 }
 
 template <class GEO>
