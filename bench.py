@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--obs-color", default="simplified", choices=["simplified", "full"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ring", type=int, default=0,
+                    help="DIAGNOSTIC: force the number of observation ring buffers (1 = L2-resident stores; not a valid bench number)")
     ap.add_argument("--masked-actions", action="store_true",
                     help="draw actions from the yaml-masked set ({0-4,8} cleanup / {0-4} harvest) instead of all n_actions")
     return ap.parse_args()
@@ -210,7 +212,7 @@ def run_b200(a):
     env = SSDBatchEnv(cfg["env"], B, n, map=cfg["map"], view_size=cfg["view_size"], episode_limit=limit,
                       extra_args=extra_args(a), seed=a.seed, device=dev, env_gid_base=rank * B)
     obs_bytes = B * env.layout.obs_env_stride
-    ring_n = max(2, int(np.ceil(2.2 * L2_BYTES / obs_bytes)))
+    ring_n = a.ring if a.ring > 0 else max(2, int(np.ceil(2.2 * L2_BYTES / obs_bytes)))
     ring = [env.new_obs_buffer() for _ in range(ring_n)]
     cfg["l2"] = f"obs written to a ring of {ring_n} buffers x {obs_bytes / 2**20:.1f} MiB (> {L2_BYTES >> 20} MiB L2), like an episode buffer"
     cfg["parallelism"] = f"env-sharded x{world} (no collective on the step path)"

@@ -450,11 +450,16 @@ __device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg
 }
 
 // ------------------------------------------------------------------ render (map_env.py:360-379, 418-446, 795-815, 923-957)
+#ifndef SSD_ST_HINT
+#define SSD_ST_HINT ""                                        // cache operator of the observation stores (see profiles/r1_notes.md)
+#endif
 __device__ __forceinline__ void st_row32(uint8_t* dst, const uint32_t* w) {     // one full 32-byte sector per lane
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+    asm volatile("st.global" SSD_ST_HINT ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
-
+__device__ __forceinline__ void st_row16(uint8_t* dst, const uint32_t* w) {
+    asm volatile("st.global" SSD_ST_HINT ".v4.b32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // raw PRMT: no selector masking
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -532,7 +537,7 @@ __device__ __forceinline__ void emit_row(const GEO& g, const KParams& p, const R
             for (int k = 0; k < 2 * OCT_T; ++k) o[k] = prmt(t0, t1, v[k]);
             o[2 * OCT_T - 1] &= lastmask;
             if (OCT_T == 4) st_row32(U.dst + pl * g.PS(), o);
-            else *reinterpret_cast<uint4*>(U.dst + pl * g.PS()) = make_uint4(o[0], o[1], o[2], o[3]);
+            else st_row16(U.dst + pl * g.PS(), o);
         }
     } else {
         const int WR = g.RP() >> 2, OCT = (WR + 1) >> 1;
