@@ -34,7 +34,6 @@ namespace {
 #define SSD_MIN_BLOCKS 8
 #endif
 constexpr int kWarps = SSD_WARPS;         // env instances per CTA
-constexpr unsigned kFull = 0xffffffffu;
 constexpr uint16_t kNoPoint = 0xFFFF;
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
@@ -182,12 +181,33 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ uint32_t pick(const uint4& v, int i) {
     return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
-// warp-strided loop with the first trip peeled (trip counts here are almost always 0 or 1)
-template <typename F>
+// A sub-warp of LPE lanes owns one env instance.  The shipped configuration is LPE = 32 (one env per warp).  LPE = 16 (two
+// envs per warp, so that the agent-lane phases issue one instruction for two envs; -DSSD_ENABLE_LPE16) passes the parity
+// suite but measured 7-20 % slower on every workload: the lane-parallel render phases take twice the trips per warp.
+// Every collective is restricted to the sub-warp's member mask, so the halves of a warp may diverge freely.
+template <int LPE>
+struct SubWarp {
+    static constexpr int kLanes = LPE, kEnvs = 32 / LPE;
+    int lane, sub, base;                                     // lane within the sub-warp, sub-warp index, first warp lane
+    unsigned mask;
+    __device__ __forceinline__ explicit SubWarp(int warp_lane)
+        : lane(warp_lane % LPE), sub(warp_lane / LPE), base(warp_lane / LPE * LPE),
+          mask(LPE == 32 ? 0xffffffffu : (0xffffu << (warp_lane / LPE * LPE))) {}
+    __device__ __forceinline__ unsigned ballot(bool pred) const { return __ballot_sync(mask, pred) >> base; }
+    template <typename T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, base + src); }
+    template <typename T> __device__ __forceinline__ unsigned match(T v) const { return __match_any_sync(mask, v) >> base; }
+    template <typename T> __device__ __forceinline__ T rmin(T v) const { return __reduce_min_sync(mask, v); }
+    template <typename T> __device__ __forceinline__ T rmax(T v) const { return __reduce_max_sync(mask, v); }
+    template <typename T> __device__ __forceinline__ T radd(T v) const { return __reduce_add_sync(mask, v); }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
+// sub-warp-strided loop with the first trip peeled (trip counts here are almost always 0 or 1)
+template <int STRIDE, typename F>
 __device__ __forceinline__ void warp_for(int n, int lane, F f) {
     int i = lane;
     if (i < n) f(i);
-    for (i += 32; i < n; i += 32) f(i);
+    for (i += STRIDE; i < n; i += STRIDE) f(i);
 }
 // bit 7 of every byte of w that differs from the corresponding byte of pat (exact, no cross-byte borrow)
 __device__ __forceinline__ uint32_t ne_bytes(uint32_t w, uint32_t pat) {
@@ -213,8 +233,8 @@ __device__ __forceinline__ int agent_colour_index(int i) {
 // ------------------------------------------------------------------ update_moves (map_env.py:477-661)
 // lanes < n hold one agent each: pos (cell index), ori, act.  Non-agent lanes carry unique
 // negative positions so they never match a cell.
-template <class GEO>
-__device__ __forceinline__ void update_moves(const GEO& g, const KParams& p, const uint8_t* __restrict__ sg, int lane, bool is_agent,
+template <class SW, class GEO>
+__device__ __forceinline__ void update_moves(const SW& w, const GEO& g, const KParams& p, const uint8_t* __restrict__ sg, int lane, bool is_agent,
                                              int act, int& pos, int& ori, int env, uint32_t gid, uint32_t tick) {
     // turns take effect immediately (map_env.py:509-511, 843-861)
     if (act == 5) ori = (0x0132 >> (4 * ori)) & 3;           // CW : LEFT->UP, RIGHT->DOWN, UP->RIGHT, DOWN->LEFT
@@ -235,34 +255,34 @@ __device__ __forceinline__ void update_moves(const GEO& g, const KParams& p, con
         SSD_CHECK(q >= 0 && q < g.G());
         prop = sg[q] == SSD_CELL_WALL ? pos : q;             // agent.py:111-119
     }
-    unsigned in_moves = __ballot_sync(kFull, mover);
+    unsigned in_moves = w.ballot(mover);
     if (in_moves == 0) return;                                // map_env.py:534
     int mv = prop;                                            // live agent_moves[i]
 
     // ---- phase 1: contested cells in lexicographic order of the ORIGINAL proposals (543-609)
-    const unsigned grp = __match_any_sync(kFull, mover ? prop : -1000 - lane);
-    unsigned pending = __ballot_sync(kFull, mover && __popc(grp) >= 2);
+    const unsigned grp = w.match(mover ? prop : -1000 - lane);
+    unsigned pending = w.ballot(mover && __popc(grp) >= 2);
     if (pending) {
         uint32_t prio = 0;
         if (mover) prio = p.d_prio ? p.d_prio[(size_t)env * p.n + lane] : philox_word(p, gid, tick, 0, (uint32_t)lane);
         while (pending) {
-            const int cell = __reduce_min_sync(kFull, ((pending >> lane) & 1u) ? prop : 0x7fffffff);
+            const int cell = w.rmin(((pending >> lane) & 1u) ? prop : 0x7fffffff);
             const bool in_cont = mover && prop == cell;
-            const unsigned cont = __ballot_sync(kFull, in_cont);
-            const unsigned occm = __ballot_sync(kFull, pos == cell);          // live positions (567)
+            const unsigned cont = w.ballot(in_cont);
+            const unsigned occm = w.ballot(pos == cell);          // live positions (567)
             bool free_cell = true;
             if (occm) {
                 const int occ = 31 - __clz(occm);                              // dict build: last index wins (516)
-                const int mv_occ = __shfl_sync(kFull, mv, occ);
+                const int mv_occ = w.shfl(mv, occ);
                 const bool occ_moves = (in_moves >> occ) & 1u;
                 const bool c1 = (cont >> occ) & 1u;                            // (1) 578
                 const bool c2 = !occ_moves || mv_occ == cell;                  // (2) 584-586
-                const unsigned swp = __ballot_sync(kFull, in_cont && mv_occ == pos);   // (3) 590-594
+                const unsigned swp = w.ballot(in_cont && mv_occ == pos);   // (3) 590-594
                 free_cell = !(c1 || c2 || swp != 0);
             }
             if (free_cell) {                                                   // winner = first in shuffled order (598-601)
-                const uint32_t mk = __reduce_min_sync(kFull, in_cont ? prio : 0xffffffffu);
-                const unsigned eq = __ballot_sync(kFull, in_cont && prio == mk);
+                const uint32_t mk = w.rmin(in_cont ? prio : 0xffffffffu);
+                const unsigned eq = w.ballot(in_cont && prio == mk);
                 if (lane == __ffs(eq) - 1) pos = cell;
             }
             if (in_cont) mv = pos;                                             // 604-609
@@ -278,19 +298,19 @@ __device__ __forceinline__ void update_moves(const GEO& g, const KParams& p, con
             const int i = __ffs(todo) - 1;
             todo &= todo - 1;
             if (!((in_moves >> i) & 1u)) continue;             // deleted earlier in this pass (619-620)
-            const int mvi = __shfl_sync(kFull, mv, i);
-            const int posi = __shfl_sync(kFull, pos, i);
-            const unsigned live = __ballot_sync(kFull, pos == mvi);            // 621
+            const int mvi = w.shfl(mv, i);
+            const int posi = w.shfl(pos, i);
+            const unsigned live = w.ballot(pos == mvi);            // 621
             if (!live) {                                                       // 650-653
                 if (lane == i) pos = mvi;
                 in_moves &= ~(1u << i);
                 continue;
             }
-            const unsigned sm = __ballot_sync(kFull, spos == mvi);
+            const unsigned sm = w.ballot(spos == mvi);
             if (!sm) { in_moves &= ~(1u << i); continue; }                     // reference KeyError; unreachable
             const int occ = 31 - __clz(sm);
-            const int pos_occ = __shfl_sync(kFull, pos, occ);
-            const int mv_occ = __shfl_sync(kFull, mv, occ);
+            const int pos_occ = w.shfl(pos, occ);
+            const int mv_occ = w.shfl(mv, occ);
             const int occ_mv = ((in_moves >> occ) & 1u) ? mv_occ : pos_occ;
             if (occ == i) in_moves &= ~(1u << i);                                              // (1) 630
             else if (!((snap >> occ) & 1u) || pos_occ == occ_mv) in_moves &= ~(1u << i);       // (2) 636-639
@@ -308,18 +328,18 @@ __device__ __forceinline__ void update_moves(const GEO& g, const KParams& p, con
 constexpr uint8_t kOcc = 0x80;
 
 // ------------------------------------------------------------------ beams (map_env.py:663-769)
-template <class GEO>
-__device__ __forceinline__ void beams(const GEO& g, const KParams& p, uint8_t* sg, int lane, bool is_agent,
+template <class SW, class GEO>
+__device__ __forceinline__ void beams(const SW& w, const GEO& g, const KParams& p, uint8_t* sg, int lane, bool is_agent,
                                       int act, int pos, int ori, int& reward, int& clean_num) {
     const bool fire = is_agent && act == 7;
     const bool clean = is_agent && act == 8 && g.kind() == SSD_KIND_CLEANUP;
     if (fire) reward -= p.fire_cost;                          // agent.py:188-190, 239-241
-    unsigned need = __ballot_sync(kFull, clean || (fire && p.hit_penalty != 0));
+    unsigned need = w.ballot(clean || (fire && p.hit_penalty != 0));
     while (need) {                                            // agent index order, map effects applied per agent (669-671)
         const int i = __ffs(need) - 1;
         need &= need - 1;
-        const int posi = __shfl_sync(kFull, pos, i), orii = __shfl_sync(kFull, ori, i);
-        const bool is_clean = __shfl_sync(kFull, act, i) == 8;
+        const int posi = w.shfl(pos, i), orii = w.shfl(ori, i);
+        const bool is_clean = w.shfl(act, i) == 8;
         // firing direction ORIENTATIONS[o] and its right-hand rotation (map_env.py:28-31, 840-841)
         const int dr = orii == 0 ? -1 : (orii == 1 ? 1 : 0), dc = orii == 2 ? -1 : (orii == 3 ? 1 : 0);
         const int rr = orii == 2 ? 1 : (orii == 3 ? -1 : 0), rc = orii == 0 ? -1 : (orii == 1 ? 1 : 0);
@@ -340,16 +360,16 @@ __device__ __forceinline__ void beams(const GEO& g, const KParams& p, uint8_t* s
                 q += d;
             }
         }
-        __syncwarp();
+        w.sync();
         if (upd >= 0) sg[upd] = (uint8_t)(SSD_CELL_RIVER | (sg[upd] & kOcc));
-        __syncwarp();
-        const unsigned um = __ballot_sync(kFull, upd >= 0);
+        w.sync();
+        const unsigned um = w.ballot(upd >= 0);
         if (lane == i && is_clean) clean_num = __popc(um);    // 672-673
         if (p.hit_penalty != 0) {                             // hit(): the LAST index standing on the cell (agent.py:184-186)
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const int hq = __shfl_sync(kFull, hit, s);
-                const unsigned on = __ballot_sync(kFull, hq >= 0 && pos == hq);
+                const int hq = w.shfl(hit, s);
+                const unsigned on = w.ballot(hq >= 0 && pos == hq);
                 if (on && lane == 31 - __clz(on)) reward -= p.hit_penalty;
             }
         }
@@ -357,14 +377,14 @@ __device__ __forceinline__ void beams(const GEO& g, const KParams& p, uint8_t* s
 }
 
 // ------------------------------------------------------------------ spawning (cleanup.py:165-204, harvest.py:92-122)
-template <class GEO>
-__device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick) {
+template <class SW, class GEO>
+__device__ __forceinline__ int spawn(const SW& w, const GEO& g, const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick) {
     const MapDev* __restrict__ m = p.map;
     uint32_t tA = 1, tW = 0;
     // one pass over the staged grid: apples (density numerator, map_env.py:291-292; none lies under an agent after
     // consume) in the high half, Cleanup's waste count (compute_permitted_area, occupancy bit ignored) in the low half
     int acc = 0;
-    warp_for(g.GS() >> 4, lane, [&](int i) {
+    warp_for<SW::kLanes>(g.GS() >> 4, lane, [&](int i) {
         uint4 v = reinterpret_cast<const uint4*>(sg)[i];
         acc += count_eq16(v, 0x02020202u) << 16;
         if (g.kind() == SSD_KIND_CLEANUP) {
@@ -372,7 +392,7 @@ __device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg
             acc += count_eq16(v, 0x03030303u);
         }
     });
-    acc = __reduce_add_sync(kFull, acc);
+    acc = w.radd(acc);
     int apples = acc >> 16;
     if (g.kind() == SSD_KIND_CLEANUP) {
         const int h = acc & 0xffff;
@@ -383,7 +403,7 @@ __device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg
     unsigned long long decided = 0;
     if (tA != 0) {
         int it = 0;
-        for (int j = lane; j < p.n_apple4; j += 32, ++it) {
+        for (int j = lane; j < p.n_apple4; j += SW::kLanes, ++it) {
             const ushort4 pts = __ldg(reinterpret_cast<const ushort4*>(m->apple_pts) + j);
             const uint16_t c4[4] = { pts.x, pts.y, pts.z, pts.w };
             uint4 r = make_uint4(0, 0, 0, 0);
@@ -414,7 +434,7 @@ __device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg
     int wcell = -1;
     if (tW != 0) {
         uint32_t bk = 0xffffffffu, bc = 0xffffffffu;
-        for (int j = lane; j < p.n_waste2; j += 32) {
+        for (int j = lane; j < p.n_waste2; j += SW::kLanes) {
             const ushort2 pts = __ldg(reinterpret_cast<const ushort2*>(m->waste_pts) + j);
             uint4 r = make_uint4(0, 0, 0, 0);
             if (!p.d_uwaste) r = philox4x32_10(gid, tick, 2u, (uint32_t)j, p.seed_lo, p.seed_hi);
@@ -428,15 +448,15 @@ __device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg
             }
         }
         const bool have = bc != 0xffffffffu;
-        if (__ballot_sync(kFull, have)) {
-            const uint32_t mk = __reduce_min_sync(kFull, have ? bk : 0xffffffffu);
-            wcell = (int)__reduce_min_sync(kFull, (have && bk == mk) ? bc : 0xffffffffu);
+        if (w.ballot(have)) {
+            const uint32_t mk = w.rmin(have ? bk : 0xffffffffu);
+            wcell = (int)w.rmin((have && bk == mk) ? bc : 0xffffffffu);
         }
     }
-    __syncwarp();                                             // every decision read the pre-spawn grid
+    w.sync();                                             // every decision read the pre-spawn grid
     if (decided) {
         int it = 0;
-        for (int j = lane; j < p.n_apple4; j += 32, ++it) {
+        for (int j = lane; j < p.n_apple4; j += SW::kLanes, ++it) {
             const ushort4 pts = __ldg(reinterpret_cast<const ushort4*>(m->apple_pts) + j);
             const uint16_t c4[4] = { pts.x, pts.y, pts.z, pts.w };
 #pragma unroll
@@ -444,8 +464,8 @@ __device__ __forceinline__ int spawn(const GEO& g, const KParams& p, uint8_t* sg
         }
     }
     if (wcell >= 0 && lane == 0) sg[wcell] = (uint8_t)(SSD_CELL_WASTE | (sg[wcell] & kOcc));
-    __syncwarp();
-    if (__ballot_sync(kFull, decided != 0)) apples += __reduce_add_sync(kFull, __popcll(decided));
+    w.sync();
+    if (w.ballot(decided != 0)) apples += w.radd(__popcll(decided));
     return apples;
 }
 
@@ -492,15 +512,15 @@ struct RowUnit {                                              // one (agent, y) 
     bool valid;
 };
 
-template <int OCT_T, class GEO>
-__device__ __forceinline__ void fetch_row(const GEO& g, const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane, int it, int units,
+template <int OCT_T, class SW, class GEO>
+__device__ __forceinline__ void fetch_row(const SW& w, const GEO& g, const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane, int it, int units,
                                           uint32_t abase_sh, int astep, RowUnit<OCT_T>& U) {
-    const int u = it * 32 + lane;
+    const int u = it * SW::kLanes + lane;
     U.valid = u < units;
     const int al = U.valid ? g.divN(u) : 0;
     const int y = u - al * g.N();
-    const uint32_t ab = __shfl_sync(kFull, abase_sh, al);
-    const int as = __shfl_sync(kFull, astep, al);
+    const uint32_t ab = w.shfl(abase_sh, al);
+    const int as = w.shfl(astep, al);
     U.w = reinterpret_cast<const uint32_t*>(pmap + (ab & 0xffffu) + (U.valid ? y * as : 0));
     U.sh = (ab >> 16) & 31u;
     U.rev = (ab >> 24) & 1u;
@@ -558,16 +578,16 @@ __device__ __forceinline__ void emit_row(const GEO& g, const KParams& p, const R
     }
 }
 
-template <int OCT_T, class GEO>
-__device__ __forceinline__ void gather_rows(const GEO& g, const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane,
+template <int OCT_T, class SW, class GEO>
+__device__ __forceinline__ void gather_rows(const SW& w, const GEO& g, const KParams& p, const uint8_t* pmap, uint8_t* gobs, int lane,
                                             uint32_t abase_sh, int astep) {
     const int WR = g.RP() >> 2;
     const uint32_t lastmask = 0xffffffffu >> (8 * (4 * WR - g.N()));
-    const int units = p.n * g.N(), iters = (units + 31) >> 5;
+    const int units = p.n * g.N(), iters = (units + SW::kLanes - 1) / SW::kLanes;
     RowUnit<OCT_T> cur, nxt;
-    fetch_row<OCT_T>(g, p, pmap, gobs, lane, 0, units, abase_sh, astep, cur);
+    fetch_row<OCT_T>(w, g, p, pmap, gobs, lane, 0, units, abase_sh, astep, cur);
     for (int it = 0; it < iters; ++it) {                      // software pipeline: row it+1 is fetched while row it is emitted
-        if (it + 1 < iters) fetch_row<OCT_T>(g, p, pmap, gobs, lane, it + 1, units, abase_sh, astep, nxt);
+        if (it + 1 < iters) fetch_row<OCT_T>(w, g, p, pmap, gobs, lane, it + 1, units, abase_sh, astep, nxt);
         emit_row<OCT_T>(g, p, cur, lastmask);
         cur = nxt;
     }
@@ -575,12 +595,12 @@ __device__ __forceinline__ void gather_rows(const GEO& g, const KParams& p, cons
 
 // Nibble-packed padded maps, built one aligned 32-bit word (8 cells) at a time.  Map cells start at nibble
 // LPn (V rounded up to 8) of a padded row, so only the last word of a row needs its tail set to "outside".
-template <class GEO>
-__device__ __forceinline__ void build_rowmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
+template <class SW, class GEO>
+__device__ __forceinline__ void build_rowmap(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
     const uint32_t* sgw = reinterpret_cast<const uint32_t*>(sg);
     const int total = g.H() * g.nw8M();
 #pragma unroll 4
-    for (int i = lane; i < total; i += 32) {
+    for (int i = lane; i < total; i += SW::kLanes) {
         const int r = g.divMW(i), j = i - r * g.nw8M();
         const int sb = r * g.W() + 8 * j, wi = sb >> 2;       // first source byte of this word (grid row r, col 8j)
         const uint32_t sel = 0x3210u + 0x1111u * (sb & 3);
@@ -594,11 +614,11 @@ __device__ __forceinline__ void build_rowmap(const GEO& g, const KParams& p, con
     }
 }
 // Transposed map: source strided by W.
-template <class GEO>
-__device__ __forceinline__ void build_colmap(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
+template <class SW, class GEO>
+__device__ __forceinline__ void build_colmap(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
     const int total = g.W() * g.nw8T();
 #pragma unroll 4
-    for (int i = lane; i < total; i += 32) {
+    for (int i = lane; i < total; i += SW::kLanes) {
         const int c = g.divMTW(i), j = i - c * g.nw8T();
         uint32_t b[8];
 #pragma unroll
@@ -612,30 +632,30 @@ __device__ __forceinline__ void build_colmap(const GEO& g, const KParams& p, con
 }
 
 // "outside the map" everywhere (utility_funcs.py:58-116 without np.pad); issued while the state loads are in flight
-template <class GEO>
-__device__ __forceinline__ void fill_outside(const GEO& g, const KParams& p, uint8_t* pmap, int lane) {
+template <class SW, class GEO>
+__device__ __forceinline__ void fill_outside(const SW& w, const GEO& g, const KParams& p, uint8_t* pmap, int lane) {
     const uint4 v6 = make_uint4(0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u);
     uint4* q = reinterpret_cast<uint4*>(pmap);
     const int n16 = g.PMS() >> 4;
 #pragma unroll 8
-    for (int i = lane; i < n16; i += 32) q[i] = v6;           // trip count is a compile-time constant for the shipped maps
+    for (int i = lane; i < n16; i += SW::kLanes) q[i] = v6;           // trip count is a compile-time constant for the shipped maps
 }
 
-template <class GEO>
-__device__ __forceinline__ void render(const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
+template <class SW, class GEO>
+__device__ __forceinline__ void render(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
                                        int lane, bool is_agent, int pos, int ori, int env) {
-    const unsigned same = __match_any_sync(kFull, pos);
+    const unsigned same = w.match(pos);
     const bool top = is_agent && lane == 31 - __clz(same);   // later index overwrites (map_env.py:370)
     int r0 = 0, c0 = 0;
     if (is_agent) { r0 = g.divW(pos); c0 = pos - r0 * g.W(); }
 
     if (p.state_rgb) {                                        // get_state: unrotated full map (map_env.py:950-957)
         uint8_t* out = p.state_rgb + (size_t)env * 3 * g.G();
-        for (int c = lane; c < g.G(); c += 32) {
+        for (int c = lane; c < g.G(); c += SW::kLanes) {
             const uint32_t rgb = lut_s[sg[c]];
             out[c] = (uint8_t)rgb; out[g.G() + c] = (uint8_t)(rgb >> 8); out[2 * g.G() + c] = (uint8_t)(rgb >> 16);
         }
-        __syncwarp();                                         // orders the agent overlay after the cell colours
+        w.sync();                                         // orders the agent overlay after the cell colours
         if (top) {
             const uint32_t rgb = lut_s[agent_colour_index(lane)];
             out[pos] = (uint8_t)rgb; out[g.G() + pos] = (uint8_t)(rgb >> 8); out[2 * g.G() + pos] = (uint8_t)(rgb >> 16);
@@ -654,38 +674,38 @@ __device__ __forceinline__ void render(const GEO& g, const KParams& p, const uin
     const uint32_t abase_sh = (uint32_t)(g.off_map(ori) + (rowc + (down ? 2 * g.V() : 0)) * pitch + ((s >> 3) << 2))
                               | ((uint32_t)((rev ? 7 - (s & 7) : (s & 7)) * 4) << 16) | ((uint32_t)rev << 24);
     const int astep = down ? -pitch : pitch;
-    const bool needT = __ballot_sync(kFull, is_agent && ori < 2) != 0, needM = __ballot_sync(kFull, is_agent && ori >= 2) != 0;
-    __syncwarp();
+    const bool needT = w.ballot(is_agent && ori < 2) != 0, needM = w.ballot(is_agent && ori >= 2) != 0;
+    w.sync();
     uint8_t* MT = pmap + g.off_map(0);
     uint8_t* M = pmap + g.off_map(2);
-    if (needM) build_rowmap(g, p, sg, M, lane);
-    if (needT) build_colmap(g, p, sg, MT, lane);
-    __syncwarp();
+    if (needM) build_rowmap(w, g, p, sg, M, lane);
+    if (needT) build_colmap(w, g, p, sg, MT, lane);
+    w.sync();
     if (top) {                                                // any cell code | 7 == 7: one atomic OR per map, no RMW race
         const int nm = g.LPn() + c0, nt = g.LPn() + r0;
         if (needM) atomicOr(reinterpret_cast<unsigned*>(M + (r0 + g.V()) * g.pitchM() + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
         if (needT) atomicOr(reinterpret_cast<unsigned*>(MT + (c0 + g.V()) * g.pitchT() + ((nt >> 3) << 2)), 7u << (4 * (nt & 7)));
     }
-    __syncwarp();
+    w.sync();
 
     uint8_t* gobs = p.obs + (size_t)env * (p.n * g.AS());
-    if (g.RP() == 32) gather_rows<4>(g, p, pmap, gobs, lane, abase_sh, astep);
-    else if (g.RP() == 16) gather_rows<2>(g, p, pmap, gobs, lane, abase_sh, astep);
-    else gather_rows<0>(g, p, pmap, gobs, lane, abase_sh, astep);
+    if (g.RP() == 32) gather_rows<4>(w, g, p, pmap, gobs, lane, abase_sh, astep);
+    else if (g.RP() == 16) gather_rows<2>(w, g, p, pmap, gobs, lane, abase_sh, astep);
+    else gather_rows<0>(w, g, p, pmap, gobs, lane, abase_sh, astep);
     const int tail = g.AS() - 3 * g.PS();                         // pad bytes per agent block (0 for the shipped views)
-    if (tail) for (int i = lane; i < p.n * (tail >> 2); i += 32)
+    if (tail) for (int i = lane; i < p.n * (tail >> 2); i += SW::kLanes)
         *reinterpret_cast<uint32_t*>(gobs + (i / (tail >> 2)) * g.AS() + 3 * g.PS() + 4 * (i % (tail >> 2))) = 0u;
     if (!p.agents_uniform) {
         // full-colour scheme: every visible agent is re-painted with its own colour (after the row stores)
-        __syncwarp();
+        w.sync();
         const uint32_t apack = (uint32_t)r0 | ((uint32_t)c0 << 10) | ((uint32_t)ori << 20);
-        const int pairs = p.n * p.n, iters = (pairs + 31) >> 5;
+        const int pairs = p.n * p.n, iters = (pairs + SW::kLanes - 1) / SW::kLanes;
         for (int it = 0; it < iters; ++it) {
-            const int q = it * 32 + lane;
+            const int q = it * SW::kLanes + lane;
             const bool valid = q < pairs;
             const int al = valid ? q / p.n : 0, j = valid ? q - al * p.n : 0;
-            const uint32_t api = __shfl_sync(kFull, apack, al), apj = __shfl_sync(kFull, apack, j);
-            const bool topj = __shfl_sync(kFull, (int)top, j);
+            const uint32_t api = w.shfl(apack, al), apj = w.shfl(apack, j);
+            const bool topj = w.shfl((int)top, j);
             if (!valid || !topj) continue;
             const int a = (int)(apj & 1023) - (int)(api & 1023) + g.V(), b = (int)((apj >> 10) & 1023) - (int)((api >> 10) & 1023) + g.V();
             if (a < 0 || a >= g.N() || b < 0 || b >= g.N()) continue;
@@ -701,19 +721,22 @@ __device__ __forceinline__ void render(const GEO& g, const KParams& p, const uin
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE, class GEO>
+template <int MODE, class GEO, int LPE>
 __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const __grid_constant__ KParams p) {
+    using SW = SubWarp<LPE>;
     const GEO g(p);
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t lut_s[16];
     if (threadIdx.x < 16) lut_s[threadIdx.x] = p.lut[threadIdx.x];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * kWarps + warp;
+    const int warp = threadIdx.x >> 5;
+    const SW w(threadIdx.x & 31);
+    const int lane = w.lane;                                  // lane within the sub-warp that owns this env
+    const int env = (blockIdx.x * kWarps + warp) * SW::kEnvs + w.sub;
     if (env >= p.B) return;
     if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
 
-    uint8_t* sg = smem + (size_t)warp * (g.GS() + g.PMS());
+    uint8_t* sg = smem + ((size_t)warp * SW::kEnvs + w.sub) * (g.GS() + g.PMS());
     uint8_t* pmap = sg + g.GS();
     const bool is_agent = lane < p.n;
     const uint32_t gid = p.gid_base + (uint32_t)env;
@@ -733,30 +756,30 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
         const uint4* src = MODE == MODE_RESET ? reinterpret_cast<const uint4*>(p.map->base_grid)
                                               : reinterpret_cast<const uint4*>(p.grid + (size_t)env * g.GS());
         if (lane < n16) g0 = src[lane];
-        if (p.obs) fill_outside(g, p, pmap, lane);
+        if (p.obs) fill_outside(w, g, p, pmap, lane);
         if (lane < n16) reinterpret_cast<uint4*>(sg)[lane] = g0;
-        for (int i = lane + 32; i < n16; i += 32) reinterpret_cast<uint4*>(sg)[i] = src[i];
+        for (int i = lane + SW::kLanes; i < n16; i += SW::kLanes) reinterpret_cast<uint4*>(sg)[i] = src[i];
     }
     if (MODE != MODE_RESET && is_agent) {
         pos = (int)(a_rec & 0xff) * g.W() + (int)((a_rec >> 8) & 0xff);
         ori = (int)((a_rec >> 16) & 3);
     }
-    __syncwarp();
+    w.sync();
 
     if (MODE == MODE_STEP) {
         int reward = 0, clean_num = 0;
-        update_moves(g, p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
+        update_moves(w, g, p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
         // consume in index order: the lowest index on a cell eats the apple (253-256); mark occupancy
-        const unsigned same = __match_any_sync(kFull, pos);
+        const unsigned same = w.match(pos);
         const int here = is_agent ? sg[pos] : 0;
-        __syncwarp();
+        w.sync();
         if (is_agent && lane == __ffs(same) - 1) {
             if (here == SSD_CELL_APPLE) { reward += 1; sg[pos] = kOcc | SSD_CELL_EMPTY; }
             else sg[pos] = (uint8_t)(kOcc | here);
         }
-        __syncwarp();
-        beams(g, p, sg, lane, is_agent, act, pos, ori, reward, clean_num);                     // 259-260
-        const int apples = spawn(g, p, sg, lane, env, gid, tick);                              // 263, 291-292
+        w.sync();
+        beams(w, g, p, sg, lane, is_agent, act, pos, ori, reward, clean_num);                     // 259-260
+        const int apples = spawn(w, g, p, sg, lane, env, gid, tick);                              // 263, 291-292
         const int t = t_prev + 1;
         if (is_agent) {
             p.reward[(size_t)env * p.n + lane] = (int8_t)reward;
@@ -780,11 +803,11 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
                 key = p.d_spawnkey ? p.d_spawnkey[((size_t)env * p.n + i) * g.G() + mycell]
                                    : philox_word(p, gid, tick, 3u, (uint32_t)(i * p.n_spawn + lane));
             const bool cand = is_sp && !taken;
-            const uint32_t mk = __reduce_max_sync(kFull, cand ? key : 0u);
-            const unsigned eq = __ballot_sync(kFull, cand && key == mk);
-            const int w = 31 - __clz(eq);
-            const int cell = __shfl_sync(kFull, mycell, w);
-            if (lane == w) taken = true;
+            const uint32_t mk = w.rmax(cand ? key : 0u);
+            const unsigned eq = w.ballot(cand && key == mk);
+            const int win = 31 - __clz(eq);
+            const int cell = w.shfl(mycell, win);
+            if (lane == win) taken = true;
             if (lane == i) pos = cell;
         }
         if (is_agent) {                                                                     // spawn_rotation (786-793)
@@ -792,25 +815,25 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
             else ori = p.d_rot ? (int)(p.d_rot[(size_t)env * p.n + lane] & 3) : (int)(philox_word(p, gid, tick, 4u, (uint32_t)lane) >> 30);
         }
         if (is_agent) sg[pos] |= kOcc;                         // distinct spawn points: no two lanes share a cell
-        __syncwarp();
-        spawn(g, p, sg, lane, env, gid, tick);                                                 // custom_map_update (313)
+        w.sync();
+        spawn(w, g, p, sg, lane, env, gid, tick);                                                 // custom_map_update (313)
         ep_ret = 0;
         if (lane == 0) { p.t[env] = 0; p.tick[env] = tick + 1; }
     }
 
     if (MODE != MODE_RENDER) {                                 // strip the occupancy bits, write the state back
-        const unsigned same = __match_any_sync(kFull, pos);
+        const unsigned same = w.match(pos);
         if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
-        __syncwarp();
+        w.sync();
         uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * g.GS());
-        warp_for(g.GS() >> 4, lane, [&](int i) { dst[i] = reinterpret_cast<const uint4*>(sg)[i]; });
+        warp_for<SW::kLanes>(g.GS() >> 4, lane, [&](int i) { dst[i] = reinterpret_cast<const uint4*>(sg)[i]; });
         if (is_agent) {
             const int r = g.divW(pos);
             p.agent[(size_t)env * p.NA + lane] = (uint32_t)r | ((uint32_t)(pos - r * g.W()) << 8) | ((uint32_t)ori << 16);
             p.ep_ret[(size_t)env * p.NA + lane] = ep_ret;
         }
     }
-    if (p.obs || p.state_rgb) render(g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
+    if (p.obs || p.state_rgb) render(w, g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
 }
 
 // ------------------------------------------------------------------ incentive bookkeeping (homophily_learner.py:98-115)
@@ -873,6 +896,7 @@ struct ssd_handle {
     size_t smem_bytes;
     int64_t launches;
     int force_generic;                                        // SSD_B200_GENERIC=1: always use the runtime-geometry kernels
+    int lanes_per_env;                                        // 16: two envs per warp (needs <= 16 spawn points); 32: one
     bool smem_attr_set[3];                                    // per kernel mode: dynamic shared-memory limit raised on this device
 };
 
@@ -888,19 +912,28 @@ static int fill_common(const ssd_handle* h, const ssd_state* st, const ssd_draws
     return SSD_OK;
 }
 
-template <int MODE, class GEO>
-static int launch_geo(ssd_handle* h, const KParams& k, void* stream) {
+template <int MODE, class GEO, int LPE>
+static int launch_lpe(ssd_handle* h, const KParams& k, void* stream) {
     DeviceGuard guard(h->device);
     SSD_CUDA(guard.err);
     if (!h->smem_attr_set[MODE]) {                            // a handle has one geometry, so one instantiation per mode
-        SSD_CUDA(cudaFuncSetAttribute(ssd_kernel<MODE, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        SSD_CUDA(cudaFuncSetAttribute(ssd_kernel<MODE, GEO, LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         h->smem_attr_set[MODE] = true;
     }
-    const int grid = (k.B + kWarps - 1) / kWarps;
-    ssd_kernel<MODE, GEO><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
+    const int envs_per_cta = kWarps * (32 / LPE);
+    const int grid = (k.B + envs_per_cta - 1) / envs_per_cta;
+    ssd_kernel<MODE, GEO, LPE><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
     ++h->launches;
     SSD_CUDA(cudaGetLastError());
     return SSD_OK;
+}
+
+template <int MODE, class GEO>
+static int launch_geo(ssd_handle* h, const KParams& k, void* stream) {
+#ifdef SSD_ENABLE_LPE16                                        // experiment: two envs per warp (measured slower, profiles/r1_notes.md)
+    if (h->lanes_per_env == 16) return launch_lpe<MODE, GEO, 16>(h, k, stream);
+#endif
+    return launch_lpe<MODE, GEO, 32>(h, k, stream);
 }
 
 // The reference's shipped geometries (constants.py maps x yaml view sizes) get compile-time index arithmetic.
@@ -1015,7 +1048,13 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     if (k.invMW20 == 0 || k.invMTW20 == 0 || k.PMS >= 60000) { delete hm; delete h; return SSD_ERR_INVALID; }
     k.off_pmap = k.GS;
     k.smem_per_warp = k.off_pmap + k.PMS;
-    h->smem_bytes = (size_t)kWarps * k.smem_per_warp;
+    // two envs per warp need the spawn points (reset) and the per-lane apple decision bits (64) to fit 16 lanes
+    h->lanes_per_env = 32;
+#ifdef SSD_ENABLE_LPE16
+    if (ns <= 16 && k.n_apple4 <= 16 * 16) h->lanes_per_env = 16;
+    { const char* e = getenv("SSD_B200_LPE"); if (e && atoi(e) == 32) h->lanes_per_env = 32; }
+#endif
+    h->smem_bytes = (size_t)kWarps * (32 / h->lanes_per_env) * k.smem_per_warp;
     { const char* e = getenv("SSD_B200_GENERIC"); h->force_generic = e && e[0] == '1'; }
     h->device = cfg->device;
 
