@@ -140,29 +140,38 @@ class BatchedEpisodeRunner:
         env_info = {"collective_return": float(coll.sum()), "equality_metric": float(eq.sum())}
         self.last_env_info = {"collective_return": coll, "equality_metric": eq}
 
-        cur_stats = self.test_stats if test_mode else self.train_stats
-        cur_returns = self.test_returns if test_mode else self.train_returns
-        log_prefix = "test_" if test_mode else ""
-        cur_stats.update({k: cur_stats.get(k, 0) + env_info.get(k, 0) for k in set(cur_stats) | set(env_info)})
-        cur_stats["n_episodes"] = B + cur_stats.get("n_episodes", 0)
-        cur_stats["ep_length"] = self.t * B + cur_stats.get("ep_length", 0)
-        if not test_mode:
-            self.t_env += self.t * B
-        cur_returns.extend(episode_return.cpu().numpy())
-        if test_mode and (len(self.test_returns) >= getattr(self.args, "test_nepisode", 1)):
-            self._log(cur_returns, cur_stats, log_prefix)
-        elif self.t_env - self.log_train_stats_t >= getattr(self.args, "runner_log_interval", 10000):
-            self._log(cur_returns, cur_stats, log_prefix)
-            if hasattr(getattr(self.mac, "action_selector", None), "epsilon"):
-                self.logger.log_stat("epsilon", self.mac.action_selector.epsilon, self.t_env)
-            self.log_train_stats_t = self.t_env
+        self._account(env_info, episode_return.cpu().numpy(), test_mode)
         return self.batch
 
-    def _log(self, returns, stats, prefix):
-        self.logger.log_stat(prefix + "return_mean", np.mean(returns), self.t_env)
-        self.logger.log_stat(prefix + "return_std", np.std(returns), self.t_env)
-        returns.clear()
-        for k, v in stats.items():
-            if k not in {"n_episodes", "clean_num", "apple_den", "agent_pos", "agent_orientation"}:
-                self.logger.log_stat(prefix + k + "_mean", v / stats["n_episodes"], self.t_env)
+    # ---- statistics: same keys and denominators as episode_runner.py:121-152, accumulated over B episodes at once ----
+    def _account(self, env_info, returns, test_mode):
+        B = self.batch_size
+        stats, rets, prefix = ((self.test_stats, self.test_returns, "test_") if test_mode
+                               else (self.train_stats, self.train_returns, ""))
+        for key in set(stats) | set(env_info):
+            stats[key] = stats.get(key, 0) + env_info.get(key, 0)
+        stats["n_episodes"] = stats.get("n_episodes", 0) + B
+        stats["ep_length"] = stats.get("ep_length", 0) + self.t * B
+        if not test_mode:
+            self.t_env += self.t * B
+        rets.extend(returns)
+        due_test = test_mode and len(self.test_returns) >= getattr(self.args, "test_nepisode", 1)
+        due_train = self.t_env - self.log_train_stats_t >= getattr(self.args, "runner_log_interval", 10000)
+        if due_test or due_train:
+            self._flush(rets, stats, prefix)
+            if not due_test:
+                eps = getattr(getattr(self.mac, "action_selector", None), "epsilon", None)
+                if eps is not None:
+                    self.logger.log_stat("epsilon", eps, self.t_env)
+                self.log_train_stats_t = self.t_env
+
+    def _flush(self, rets, stats, prefix):
+        log = self.logger.log_stat
+        log(prefix + "return_mean", np.mean(rets), self.t_env)
+        log(prefix + "return_std", np.std(rets), self.t_env)
+        episodes = stats["n_episodes"]
+        skip = {"n_episodes", "clean_num", "apple_den", "agent_pos", "agent_orientation"}
+        for key in [k for k in stats if k not in skip]:
+            log(prefix + key + "_mean", stats[key] / episodes, self.t_env)
+        rets.clear()
         stats.clear()
