@@ -86,3 +86,41 @@ def test_fakebatch_has_the_update_semantics_of_the_reference_episodebatch():
     for k in fs:
         assert torch.equal(ref[k], fake[k]) and ref[k].dtype == fake[k].dtype, k
     assert torch.equal(ref["filled"], fake["filled"])
+
+
+def test_hit_penalty_and_fire_cost_semantics_against_patched_reference():
+    """north_star 'penalties': the reference hard-codes hit -= 0 / fire -= 1 (agent.py:184-190, 239-248).  Patching just
+    those two constants in the live reference pins the oracle's fire_cost / hit_penalty parameters (who gets hit: the
+    agent `agent_by_pos` returns, i.e. the last index on the cell)."""
+    import numpy as np
+    from homophily_marl_b200 import mapspec
+    from oracle.oracle import OracleBatch
+    RefBackend = _ref_backend()
+    refshim._import_registry()
+    import envs.ssd.agent as ag
+
+    def hit(self, char):
+        if char == 'F':
+            self.reward_this_turn -= 5
+
+    def fire_beam(self, char):
+        if char == 'F':
+            self.reward_this_turn -= 2
+
+    saved = (ag.HarvestAgent.hit, ag.HarvestAgent.fire_beam)
+    ag.HarvestAgent.hit, ag.HarvestAgent.fire_beam = hit, fire_beam
+    try:
+        key = "harvest10_full"
+        ref = RefBackend(key, random_spawn=True)
+        spec = mapspec.compile_map("harvest", "default10", 10, 7, 1000, obs_color="full", fire_cost=2, hit_penalty=5)
+        ora = ls.OracleBackend(key, random_spawn=True)
+        ora.o = OracleBatch.from_spec(spec, n_envs=1, random_spawn_point=True, spawn_rotation=None)
+        sched_a = ls.schedule_for(key, 77, teleport_every=4)
+        sched_b = ls.schedule_for(key, 77, teleport_every=4)
+        sched_a.n_actions = sched_b.n_actions = 8
+        a = ls.run_trace(ref, sched_a, 120)
+        b = ls.run_trace(ora, sched_b, 120)
+        ls.assert_traces_equal(a, b, "penalties")
+        assert (a["reward"] <= -5).any() and (a["reward"] == -2).any()
+    finally:
+        ag.HarvestAgent.hit, ag.HarvestAgent.fire_beam = saved
