@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--obs-color", default="simplified", choices=["simplified", "full"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-groups-probe", action="store_true", help="skip the informational pipelined-groups measurement")
     ap.add_argument("--ring", type=int, default=0,
                     help="DIAGNOSTIC: force the number of observation ring buffers (1 = L2-resident stores; not a valid bench number)")
     ap.add_argument("--masked-actions", action="store_true",
@@ -195,6 +196,52 @@ def run_reference(a):
 
 
 # --------------------------------------------------------------------------- CUDA arm
+def pipelined_groups_probe(cfg, a, dev, rank, groups=4, steps=400):
+    """Informational: the same envs stepped as `groups` independent sub-batches on separate streams (double-buffered
+    rollout, what an asynchronous sampler does).  The logic phase of one group overlaps the observation stores of another."""
+    import torch
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    B, n = cfg["envs_per_gpu"], cfg["num_agents"]
+    if B % groups:
+        return None
+    Bg = B // groups
+    envs = [SSDBatchEnv(cfg["env"], Bg, n, map=cfg["map"], view_size=cfg["view_size"], episode_limit=10 ** 6,
+                        extra_args=extra_args(a), seed=a.seed, device=dev, env_gid_base=rank * B + g * Bg) for g in range(groups)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(groups)]
+    ring_n = max(2, int(np.ceil(2.2 * L2_BYTES / (B * envs[0].layout.obs_env_stride))))
+    graphs = []
+    for g, (e, s) in enumerate(zip(envs, streams)):
+        acts = torch.randint(0, e.n_actions, (32, Bg, n), device=dev, dtype=torch.int32).to(torch.uint8)
+        ring = [e.new_obs_buffer() for _ in range(ring_n)]
+        with torch.cuda.stream(s):
+            e.reset()
+            for i in range(3):
+                e.step(acts[i], obs_out=ring[i % ring_n])
+            s.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                for i in range(steps):
+                    e.step(acts[i % 32], obs_out=ring[i % ring_n])
+        graphs.append((gr, acts, ring))
+    torch.cuda.synchronize()
+    ms = float("inf")
+    for _ in range(3):                                        # the first replay also uploads the graphs
+        e0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(groups)]
+        e0.record()
+        for g in range(groups):
+            streams[g].wait_event(e0)
+            with torch.cuda.stream(streams[g]):
+                graphs[g][0].replay()
+                ends[g].record(streams[g])
+        torch.cuda.synchronize()
+        ms = min(ms, max(e0.elapsed_time(x) for x in ends))
+    for e in envs:
+        e.close()
+    return {"groups": groups, "steps": steps, "value": B * n * steps / (ms * 1e-3), "unit": "agent-steps/s",
+            "us_per_step": ms / steps * 1e3, "what": f"{groups} independent groups of {Bg} envs on {groups} streams (same global env ids)"}
+
+
 def run_b200(a):
     import torch
     rank, local_rank, world = dist_env()
@@ -339,6 +386,8 @@ def run_b200(a):
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "bytes_per_env_step": env.bytes_per_env_step(),
                              "avg_launch_us": avg_launch_s * 1e6}}
+        if world == 1 and not a.no_groups_probe:
+            line["pipelined_groups"] = pipelined_groups_probe(cfg, a, dev, rank)
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = time_oracle(cfg, a, steps=20, warmup=3, budget_s=20.0, threads=threads)
