@@ -10,8 +10,8 @@ from homophily_marl_b200.batch_env import SSDBatchEnv  # noqa: E402
 
 B, n, T = 4096, 5, 400
 out = {}
-for G in (1, 2, 4):
-    for offset in (False, True):
+for G in (1, 2, 4, 8, 16):
+    for offset in (False,):
         if G == 1 and offset:
             continue
         Bg = B // G
