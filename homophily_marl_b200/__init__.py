@@ -8,13 +8,20 @@ The compute path is the CUDA library ``libssd_b200.so`` (C ABI: include/ssd_b200
 """
 from . import mapspec  # noqa: F401
 
-__all__ = ["mapspec", "SSDBatchEnv", "REGISTRY", "CleanupEnv", "HarvestEnv", "MultiAgentEnv"]
+__all__ = ["mapspec", "SSDBatchEnv", "BatchedEpisodeRunner", "incentive_rewards", "REGISTRY", "CleanupEnv", "HarvestEnv",
+           "MultiAgentEnv"]
 
 
 def __getattr__(name):
     if name == "SSDBatchEnv":
         from .batch_env import SSDBatchEnv
         return SSDBatchEnv
+    if name == "BatchedEpisodeRunner":
+        from .batched_runner import BatchedEpisodeRunner
+        return BatchedEpisodeRunner
+    if name == "incentive_rewards":
+        from .incentive import incentive_rewards
+        return incentive_rewards
     if name in ("REGISTRY", "CleanupEnv", "HarvestEnv", "MultiAgentEnv"):
         from . import pymarl_env
         return getattr(pymarl_env, name)

@@ -353,3 +353,21 @@ def test_single_env_1000_steps_like_baseline_config0():
         obs_sum += int(out["obs"].sum())
     assert bool(env.done[0].item()) and obs_sum > 0
     assert np.array_equal(env.ep_ret.cpu().numpy(), ora.ep_ret)
+
+
+def test_incentive_python_wrapper():
+    from homophily_marl_b200.incentive import incentive_rewards
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    a = torch.randint(0, 3, (4, 7, 3, 3, 1), generator=g).to(dev)
+    r = torch.randint(-1, 2, (4, 7, 3), generator=g).float().to(dev)
+    mask = (1 - torch.eye(3, device=dev)).view(1, 1, 3, 3, 1).long()
+    am = a * mask
+    give = (am != 0).sum(dim=(3, 4))
+    rv = (am == 1).sum(dim=(2, 4)) - (am == 2).sum(dim=(2, 4))
+    env_r, inc_r, sgn = incentive_rewards(a, r, 1.0, 0.5, 2.0, 101, recip=True)
+    assert env_r.shape == r.shape and torch.equal(sgn, torch.sign(rv.float()))
+    assert torch.allclose(env_r, (r + rv * 2.0 * 1.0) / 101, rtol=0, atol=1e-7)
+    assert torch.allclose(inc_r, (r - give * 0.5 * 1.0) / 101, rtol=0, atol=1e-7)
+    with pytest.raises(RuntimeError):
+        incentive_rewards(a.cpu(), r.cpu(), 1.0, 0.5, 2.0, 101)
