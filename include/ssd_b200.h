@@ -139,7 +139,8 @@ int ssd_reset(ssd_handle* h, const ssd_state* st, const uint8_t* mask, const ssd
               uint8_t* obs, void* stream);
 
 /* MapEnv.step (map_env.py:874-915 -> _step 227-295) fused with get_obs (923-945) and,
- * optionally, get_state (950-957).  actions: [B][n] u8, values < n_actions. */
+ * optionally, get_state (950-957).  actions: [B][n] u8, values < n_actions; a larger value makes that agent do
+ * nothing this step (the reference raises KeyError, which the Python facade reproduces before calling). */
 int ssd_step(ssd_handle* h, const ssd_state* st, const uint8_t* actions, const ssd_draws* draws,
              const ssd_step_out* out, void* stream);
 
