@@ -108,3 +108,25 @@ def test_checked_build_sees_no_shared_memory_violation():
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, "SSD_B200_CHECKED": "1"},
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OOB 0" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("B,n", [(1, 1), (3, 1), (5, 2), (4097, 5)])
+def test_ragged_batch_sizes_and_single_agent(B, n):
+    """Batch sizes that do not fill the last CTA, and a single agent (no conflicts, every lane but one idle)."""
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    extra = dict(random_spawn_point=True, random_spawn_rotation=None)
+    env = SSDBatchEnv("harvest", B, n, map="default10", view_size=15, episode_limit=9, seed=31, extra_args=extra)
+    ora = O.OracleBatch.from_spec(env.spec, n_envs=B, seed=31, random_spawn_point=True, spawn_rotation=None)
+    env.reset()
+    ora.reset(threads=8)
+    rs = np.random.RandomState(B)
+    for t in range(12):
+        act = rs.randint(0, 8, size=(B, n)).astype(np.uint8)
+        env.step(torch.as_tensor(act, device=env.device))
+        out = ora.step(act, threads=8)
+        assert np.array_equal(env.reward.cpu().numpy(), out["reward"]) and np.array_equal(env.done.cpu().numpy(), out["done"])
+        assert np.array_equal(env.obs_view().cpu().numpy(), out["obs"]), t
+        if out["done"].all():
+            env.reset()
+            ora.reset(threads=8)
+    assert np.array_equal(env.grid.cpu().numpy(), ora.grid)
