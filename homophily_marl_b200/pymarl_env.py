@@ -111,6 +111,7 @@ class _SSDEnv(MultiAgentEnv):
         lay = self.sim.layout
         self._obs_host = self._io["obs"].numpy().reshape(-1)[: lay.obs_env_stride]
         self._obs_strides = (lay.obs_agent_stride, lay.obs_plane_stride, lay.obs_row_stride, 1)
+        self._act_host = self._io["actions"].numpy()[0]   # NumPy view of the pinned action row
         self.sim.reset()                                # valid state before the first reset() ...
         self.sim.tick_buf.zero_()                       # ... which then replays the same draws (tick 0)
         self.sim.pull_host(self._io)
@@ -118,12 +119,15 @@ class _SSDEnv(MultiAgentEnv):
     # ------------------------------------------------------------------ step / reset
     def step(self, actions):
         """Returns reward, terminated, info (map_env.py:874-915)."""
-        acts = [int(a) for a in actions]
+        if isinstance(actions, torch.Tensor):            # the runner passes a device LongTensor [n, 1]: one D2H, not n
+            acts = [int(a) for a in actions.reshape(-1).tolist()]
+        else:
+            acts = [int(a) for a in actions]
         for a in acts[:self.num_agents]:
             if not 0 <= a < self.n_actions:
                 raise KeyError(a)                        # agent.py:176,237 action_map lookup
         io, sim = self._io, self.sim
-        io["actions"][0] = torch.tensor(acts[:self.num_agents], dtype=torch.uint8)
+        self._act_host[:] = acts[:self.num_agents]
         sim.step_host(io)                                # H2D actions, fused step+obs+state kernel, D2H results, sync
         sim.pull_host(io, obs=False, state=False, agent=True)
         reward = io["reward"][0].numpy().astype(float)

@@ -22,7 +22,7 @@ for name, mp, n, view in (("cleanup", "default3", 3, 7), ("cleanup", "default5",
             term = False
             while not term:
                 env.get_state(); env.get_avail_actions(); env.get_obs(); env.get_agent_pos(); env.get_agent_orientation()
-                r, term, info = env.step(torch.as_tensor(rs.randint(0, 5, size=(n, 1))))
+                r, term, info = env.step(torch.as_tensor(rs.randint(0, 5, size=(n, 1)), device='cuda'))   # like the MAC's output
                 env.get_agent_pos()
                 steps += 1
         torch.cuda.synchronize()
