@@ -1,0 +1,1 @@
+"""stub: see matplotlib/__init__.py"""

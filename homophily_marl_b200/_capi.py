@@ -16,7 +16,7 @@ SSD_OK, SSD_ERR_INVALID, SSD_ERR_CUDA, SSD_ERR_SPAWN, SSD_ERR_MAP = 0, -1, -2, -
 
 # every symbol include/ssd_b200.h declares (checked by tests/test_capi_symbols.py against the header text)
 EXPORTS = ("ssd_abi_version", "ssd_error_string", "ssd_last_cuda_error", "ssd_prob_to_threshold",
-           "ssd_create", "ssd_destroy", "ssd_get_layout", "ssd_reset", "ssd_step", "ssd_render",
+           "ssd_create", "ssd_destroy", "ssd_get_layout", "ssd_reset", "ssd_step", "ssd_step_range", "ssd_render",
            "ssd_step_host", "ssd_incentive", "ssd_launch_count", "ssd_debug_oob_count")
 
 
@@ -78,6 +78,8 @@ def load():
     L.ssd_get_layout.argtypes = [C.c_void_p, C.POINTER(SsdLayout)]
     L.ssd_reset.argtypes = [C.c_void_p, C.POINTER(SsdState), C.c_void_p, C.POINTER(SsdDraws), C.c_void_p, C.c_void_p]
     L.ssd_step.argtypes = [C.c_void_p, C.POINTER(SsdState), C.c_void_p, C.POINTER(SsdDraws), C.POINTER(SsdStepOut), C.c_void_p]
+    L.ssd_step_range.argtypes = [C.c_void_p, C.POINTER(SsdState), C.c_void_p, C.POINTER(SsdDraws), C.POINTER(SsdStepOut),
+                                 C.c_int32, C.c_int32, C.c_void_p]
     L.ssd_render.argtypes = [C.c_void_p, C.POINTER(SsdState), C.c_void_p, C.c_void_p, C.c_void_p]
     L.ssd_step_host.argtypes = [C.c_void_p, C.POINTER(SsdState), C.c_void_p, C.c_void_p,
                                 C.POINTER(SsdStepOut), C.POINTER(SsdStepOut), C.c_void_p]

@@ -11,6 +11,7 @@ Replaces, batched: MapEnv.reset / step / get_obs / get_state
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -34,7 +35,7 @@ def _ptr(t):
 class SSDBatchEnv:
     def __init__(self, name, n_envs, num_agents, map="default", view_size=7, episode_limit=100,
                  extra_args=None, seed=0, device="cuda:0", env_gid_base=0, rows=None, params=None,
-                 fire_cost=1, hit_penalty=0, want_state=False):
+                 fire_cost=1, hit_penalty=0, want_state=False, check_actions=False):
         extra = dict(random_spawn_point=False, random_spawn_rotation=0, disable_rotation_action=True,
                      disable_fire_action=True, obs_color="simplified")
         extra.update(extra_args or {})
@@ -44,6 +45,8 @@ class SSDBatchEnv:
                                         obs_color=extra["obs_color"], rows=rows, params=params,
                                         fire_cost=fire_cost, hit_penalty=hit_penalty)
         self.device = _require_cuda(device)
+        # debug switch (one device sync per step): out-of-range action codes raise KeyError like the reference's action_map
+        self.check_actions = bool(check_actions) or os.environ.get("SSD_B200_CHECK_ACTIONS") == "1"
         self.lib = _capi.load()
         s = self.spec
         self.B, self.n, self.H, self.W, self.G, self.N = int(n_envs), s.n_agents, s.H, s.W, s.G, s.N
@@ -187,6 +190,13 @@ class SSDBatchEnv:
         _capi.check(self.lib.ssd_reset(self._h, C.byref(self._st), _ptr(mask), C.byref(d) if d else None,
                                        _ptr(out), self._stream()))
 
+    def _check_actions(self, actions):
+        if actions.dtype != torch.uint8 or not actions.is_cuda or not actions.is_contiguous() or actions.numel() != self.B * self.n:
+            raise ValueError("actions must be a contiguous uint8 CUDA tensor of shape [B, n]")
+        if self.check_actions and bool((actions >= self.n_actions).any()):
+            # the reference raises KeyError from action_map (agent.py:176,237); the kernel alone would treat the code as a no-op
+            raise KeyError(int(actions.max()))
+
     def _step_out(self, obs_out, want_obs, want_state):
         return _capi.SsdStepOut(self.reward.data_ptr(), self.clean.data_ptr(), self.apple_cnt.data_ptr(),
                                 self.done.data_ptr(),
@@ -195,12 +205,21 @@ class SSDBatchEnv:
 
     def step(self, actions, draws=None, obs_out=None, want_obs=True, want_state=False):
         """actions: u8 CUDA tensor [B, n].  Results land in self.reward / clean / apple_cnt / done / obs."""
-        if actions.dtype != torch.uint8 or not actions.is_cuda or not actions.is_contiguous() or actions.numel() != self.B * self.n:
-            raise ValueError("actions must be a contiguous uint8 CUDA tensor of shape [B, n]")
+        self._check_actions(actions)
         d = self._draws(draws)
         so = self._step_out(obs_out, want_obs, want_state)
         _capi.check(self.lib.ssd_step(self._h, C.byref(self._st), _ptr(actions), C.byref(d) if d else None,
                                       C.byref(so), self._stream()))
+
+    def step_range(self, actions, env_begin, env_count, draws=None, obs_out=None, want_obs=True, want_state=False):
+        """``step`` restricted to envs [env_begin, env_begin + env_count) (``ssd_step_range``).  ``actions`` is the
+        whole-batch [B, n] tensor; disjoint ranges may run concurrently on different CUDA streams (the launch goes to the
+        caller's current stream), which lets one group's policy / logic overlap another group's observation stores."""
+        self._check_actions(actions)
+        d = self._draws(draws)
+        so = self._step_out(obs_out, want_obs, want_state)
+        _capi.check(self.lib.ssd_step_range(self._h, C.byref(self._st), _ptr(actions), C.byref(d) if d else None,
+                                            C.byref(so), int(env_begin), int(env_count), self._stream()))
 
     def render(self, obs_out=None, want_obs=True, want_state=False):
         o = (self.obs_buf if obs_out is None else obs_out) if want_obs else None

@@ -11,7 +11,9 @@ Differences that follow from B > 1 (all envs share ``episode_limit`` and termina
 constantly False in the reference, agent.py:192,243):
   * ``t_env`` advances by ``B * t`` per call (total env steps), ``n_episodes`` by B;
   * ``collective_return`` / ``equality_metric`` are summed over the B envs into the stats dict exactly as B
-    successive single-env episodes would.
+    successive single-env episodes would;
+  * the step loop never synchronises with the host: ``terminated`` is the host-side step count (all envs share
+    ``episode_limit``), and the state image comes out of the same launch as the step (``ssd_step_out.state_rgb``).
 """
 from __future__ import annotations
 
@@ -81,12 +83,12 @@ class BatchedEpisodeRunner:
     def reset(self):
         self.batch = self.new_batch()
         self.env.reset()
+        self.env.render(want_obs=False, want_state=True)      # get_state() of the fresh episode; later states come from step
         self.t = 0
 
     # ---- device-side views of what the reference env returns per step -------------------------------------
     def _pre_transition(self):
-        e = self.env
-        e.render(want_obs=False, want_state=True)             # get_state(); obs are already rendered by step/reset
+        e = self.env                                          # obs AND state image were written by the last step / reset launch
         return {"state": e.state_rgb.float() / 256, "avail_actions": self._avail,
                 "obs": e.obs_view().float() / 256, "agent_pos": e.agent_pos.float(),
                 "agent_orientation": self._orient_vec[e.agent_orient.long()]}
@@ -108,10 +110,13 @@ class BatchedEpisodeRunner:
             else:
                 actions = self.mac.select_actions(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
             actions_env = actions % self.args.n_actions
-            e.step(actions_env.reshape(B, e.n).to(device=e.device, dtype=torch.uint8).contiguous())
+            e.step(actions_env.reshape(B, e.n).to(device=e.device, dtype=torch.uint8).contiguous(), want_state=True)
             reward = e.reward.float()
             episode_return += reward
-            terminated = bool(e.done[0].item())               # the one host sync per step: all envs end together
+            # no host sync in the step loop: every env shares episode_limit and get_done() is constantly False in the
+            # reference (agent.py:192,243; map_env.py:890-894), so `terminated` is a host-side step count; the device-side
+            # `done` flags (what goes into the batch) are checked against it once per episode below
+            terminated = self.t + 1 >= self.episode_limit
             post = {"actions": actions, "reward": reward if getattr(self.args, "ind_reward", True) else reward.sum(1, keepdim=True),
                     "terminated": e.done.view(B, 1), "clean_num": e.clean.float(),
                     "apple_den": (e.apple_cnt.to(torch.int32) & 0xFFFF).double().view(B, 1).expand(B, e.n) / e.G}
@@ -132,6 +137,8 @@ class BatchedEpisodeRunner:
         self.batch.update({"actions": actions}, ts=self.t)
 
         # termination info of every env (map_env.py:897-912), accumulated like B single-env episodes
+        if not bool(e.done.all().item()):                     # first host sync of the episode
+            raise RuntimeError("device-side done flags disagree with the host step count")
         R = e.ep_ret.double().cpu().numpy()
         coll = R.sum(axis=1)
         denom = 2 * e.n * np.abs(R).sum(axis=1)

@@ -22,6 +22,7 @@
 #include <string.h>
 #include <math.h>
 #include <new>
+#include <mutex>
 
 #include "ssd_b200.h"
 
@@ -35,6 +36,7 @@ namespace {
 #endif
 constexpr int kWarps = SSD_WARPS;         // env instances per CTA
 constexpr uint16_t kNoPoint = 0xFFFF;
+constexpr int kMaxDevices = 64;
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
 
@@ -59,6 +61,7 @@ struct MapDev {
 
 struct KParams {
     int kind, B, n, H, W, G, V, N;
+    int env0, env1;                           // this launch covers env instances [env0, env1) of the B resident ones
     int GS, NA, RP, PS, AS, ES;               // strides (ssd_layout)
     int pitchM, pitchT, off_map[4], PMS;      // nibble maps M / MT: row pitches, byte offset by orientation (0,1 -> MT; 2,3 -> M), total bytes
     int LPn, nw8M, nw8T;                      // left pad in nibbles (V rounded up to 8), words per map row holding cells
@@ -732,8 +735,8 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
     const int warp = threadIdx.x >> 5;
     const SW w(threadIdx.x & 31);
     const int lane = w.lane;                                  // lane within the sub-warp that owns this env
-    const int env = (blockIdx.x * kWarps + warp) * SW::kEnvs + w.sub;
-    if (env >= p.B) return;
+    const int env = p.env0 + (blockIdx.x * kWarps + warp) * SW::kEnvs + w.sub;
+    if (env >= p.env1) return;
     if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
 
     uint8_t* sg = smem + ((size_t)warp * SW::kEnvs + w.sub) * (g.GS() + g.PMS());
@@ -897,12 +900,12 @@ struct ssd_handle {
     int64_t launches;
     int force_generic;                                        // SSD_B200_GENERIC=1: always use the runtime-geometry kernels
     int lanes_per_env;                                        // 16: two envs per warp (needs <= 16 spawn points); 32: one
-    bool smem_attr_set[3];                                    // per kernel mode: dynamic shared-memory limit raised on this device
 };
 
 static int fill_common(const ssd_handle* h, const ssd_state* st, const ssd_draws* d, KParams& k) {
     if (!h || !st || !st->grid || !st->agent || !st->ep_ret || !st->t || !st->tick) return SSD_ERR_INVALID;
     k = h->kp;
+    k.env0 = 0; k.env1 = k.B;
     k.grid = st->grid; k.agent = st->agent; k.ep_ret = st->ep_ret; k.t = st->t; k.tick = st->tick;
     if (d) {
         if ((d->u_waste == nullptr) != (d->wkey == nullptr)) return SSD_ERR_INVALID;
@@ -916,12 +919,21 @@ template <int MODE, class GEO, int LPE>
 static int launch_lpe(ssd_handle* h, const KParams& k, void* stream) {
     DeviceGuard guard(h->device);
     SSD_CUDA(guard.err);
-    if (!h->smem_attr_set[MODE]) {                            // a handle has one geometry, so one instantiation per mode
-        SSD_CUDA(cudaFuncSetAttribute(ssd_kernel<MODE, GEO, LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        h->smem_attr_set[MODE] = true;
+    {   // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel FUNCTION (per device), not to a handle: all
+        // runtime-geometry handles share one instantiation, so the limit is only ever raised (high-water mark).
+        static std::mutex mu;
+        static int high_water[kMaxDevices] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        const int dev = h->device;
+        if (dev < 0 || dev >= kMaxDevices) return SSD_ERR_INVALID;
+        if ((int)h->smem_bytes > high_water[dev]) {
+            SSD_CUDA(cudaFuncSetAttribute(ssd_kernel<MODE, GEO, LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+            high_water[dev] = (int)h->smem_bytes;
+        }
     }
     const int envs_per_cta = kWarps * (32 / LPE);
-    const int grid = (k.B + envs_per_cta - 1) / envs_per_cta;
+    const int grid = (k.env1 - k.env0 + envs_per_cta - 1) / envs_per_cta;
+    if (grid <= 0) return SSD_OK;
     ssd_kernel<MODE, GEO, LPE><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
     ++h->launches;
     SSD_CUDA(cudaGetLastError());
@@ -1060,6 +1072,11 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
 
     DeviceGuard guard(cfg->device);
     cudaError_t e = guard.err;
+    if (e == cudaSuccess) {                                   // the launch needs smem_bytes dynamic + the static LUT
+        int optin = 0;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+        if (e == cudaSuccess && h->smem_bytes + 256 > (size_t)optin) { delete hm; delete h; return SSD_ERR_INVALID; }
+    }
     if (e == cudaSuccess) e = cudaMalloc(&h->d_map, sizeof(MapDev));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_map, hm, sizeof(MapDev), cudaMemcpyHostToDevice);
     delete hm;
@@ -1104,6 +1121,19 @@ int ssd_step(ssd_handle* h, const ssd_state* st, const uint8_t* actions, const s
     const int rc = fill_common(h, st, draws, k);
     if (rc) return rc;
     if (!actions || !out || !out->reward || !out->clean || !out->apple_cnt || !out->done) return SSD_ERR_INVALID;
+    k.actions = actions; k.reward = out->reward; k.clean = out->clean; k.apple_cnt = out->apple_cnt; k.done = out->done;
+    k.obs = out->obs; k.state_rgb = out->state_rgb;
+    return launch<MODE_STEP>(h, k, stream);
+}
+
+int ssd_step_range(ssd_handle* h, const ssd_state* st, const uint8_t* actions, const ssd_draws* draws,
+                   const ssd_step_out* out, int32_t env_begin, int32_t env_count, void* stream) {
+    KParams k;
+    const int rc = fill_common(h, st, draws, k);
+    if (rc) return rc;
+    if (!actions || !out || !out->reward || !out->clean || !out->apple_cnt || !out->done) return SSD_ERR_INVALID;
+    if (env_begin < 0 || env_count < 0 || (int64_t)env_begin + env_count > k.B) return SSD_ERR_INVALID;
+    k.env0 = env_begin; k.env1 = env_begin + env_count;
     k.actions = actions; k.reward = out->reward; k.clean = out->clean; k.apple_cnt = out->apple_cnt; k.done = out->done;
     k.obs = out->obs; k.state_rgb = out->state_rgb;
     return launch<MODE_STEP>(h, k, stream);

@@ -88,10 +88,12 @@ class _SSDEnv(MultiAgentEnv):
         extra = dict(random_spawn_point=False, random_spawn_rotation=0, disable_rotation_action=True,
                      disable_fire_action=True, obs_color="simplified")
         extra.update(extra_args or {})
+        # `ascii_map` is accepted and IGNORED, as in the reference: CleanupEnv / HarvestEnv replace it with the map that
+        # `map=` selects (cleanup.py:31-54, harvest.py:18-22).  Custom maps: SSDBatchEnv(rows=...).
         device = device or os.environ.get("SSD_B200_DEVICE", "cuda:0")
         self.sim = SSDBatchEnv(self.ENV_NAME, 1, num_agents, map=map, view_size=view_size,
                                episode_limit=episode_limit, extra_args=extra, seed=0 if seed is None else int(seed),
-                               device=device, rows=ascii_map, want_state=True, env_gid_base=env_gid_base)
+                               device=device, want_state=True, env_gid_base=env_gid_base)
         if not quiet:                                   # cleanup.py:56-58 / harvest.py:24-26
             print("map difficulty: {}".format(map))
             for row in self.sim.spec.rows:

@@ -13,7 +13,7 @@
  * pointers unless the name starts with h_ (host, pinned); `stream` is a
  * cudaStream_t passed as void*; every call returns 0 or a negative SSD_ERR_*
  * code and never throws; no internal threads; calls on one handle must be
- * serialised by the caller.  There is no CPU fallback: without a CUDA device
+ * serialised by the caller (except ssd_step_range on disjoint ranges).  There is no CPU fallback: without a CUDA device
  * ssd_create fails with SSD_ERR_CUDA.
  */
 #ifndef SSD_B200_H
@@ -143,6 +143,13 @@ int ssd_reset(ssd_handle* h, const ssd_state* st, const uint8_t* mask, const ssd
  * nothing this step (the reference raises KeyError, which the Python facade reproduces before calling). */
 int ssd_step(ssd_handle* h, const ssd_state* st, const uint8_t* actions, const ssd_draws* draws,
              const ssd_step_out* out, void* stream);
+
+/* ssd_step restricted to the env instances [env_begin, env_begin + env_count).  Every pointer is still the base of the
+ * whole-batch buffer.  Independent ranges may be stepped concurrently on different streams (an asynchronous sampler
+ * that overlaps the policy of one group with the env step of another); a range's trajectory does not depend on how the
+ * batch is split, because draws are keyed by the global env id. */
+int ssd_step_range(ssd_handle* h, const ssd_state* st, const uint8_t* actions, const ssd_draws* draws,
+                   const ssd_step_out* out, int32_t env_begin, int32_t env_count, void* stream);
 
 /* get_obs / get_state without stepping (map_env.py:923-957).  Either pointer may be NULL. */
 int ssd_render(ssd_handle* h, const ssd_state* st, uint8_t* obs, uint8_t* state_rgb, void* stream);
