@@ -123,6 +123,9 @@ def register_b200() -> None:
         ref_envs._reference_registry = dict(ref_envs.REGISTRY)
     ref_envs.REGISTRY.update(pymarl_env.REGISTRY)
     ref_runners.REGISTRY["batched"] = BatchedEpisodeRunner
+    import components.action_selectors as ref_selectors
+    from homophily_marl_b200 import selectors
+    ref_selectors.REGISTRY.update(selectors.REGISTRY)        # 'epsilon_greedy_b200': one kernel instead of seven torch launches
 
 
 def _python_bool_terminated(ctor):

@@ -12,6 +12,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 SRC = os.path.join(PKG_DIR, "csrc", "ssd_b200.cu")
+SRCS = [SRC, os.path.join(PKG_DIR, "csrc", "policy_b200.cu")]
 HDR = os.path.join(ROOT, "include", "ssd_b200.h")
 LIB = os.path.join(PKG_DIR, "libssd_b200.so")
 
@@ -30,7 +31,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in (SRC, HDR))
+    return any(os.path.getmtime(f) > t for f in SRCS + [HDR])
 
 
 LIB_CHECK = os.path.join(PKG_DIR, "libssd_b200_check.so")
@@ -38,7 +39,7 @@ LIB_CHECK = os.path.join(PKG_DIR, "libssd_b200_check.so")
 
 def build_checked(force: bool = False) -> str:
     """Variant with -DSSD_BOUNDS_CHECK (own shared-memory index checks; see ssd_debug_oob_count)."""
-    if not force and os.path.exists(LIB_CHECK) and os.path.getmtime(LIB_CHECK) >= max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+    if not force and os.path.exists(LIB_CHECK) and os.path.getmtime(LIB_CHECK) >= max(os.path.getmtime(f) for f in SRCS + [HDR]):
         return LIB_CHECK
     return build(force=True, extra_flags=["-DSSD_BOUNDS_CHECK"], out=LIB_CHECK)
 
@@ -46,7 +47,7 @@ def build_checked(force: bool = False) -> str:
 def build(force: bool = False, extra_flags=(), verbose: bool = False, out: str = LIB) -> str:
     if not force and out == LIB and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", out, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", out] + SRCS
     env = dict(os.environ)
     if os.path.exists("/usr/bin/gcc"):
         cmd += ["-ccbin", "/usr/bin/g++"]
@@ -61,3 +62,4 @@ def build(force: bool = False, extra_flags=(), verbose: bool = False, out: str =
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_checked(force=True))                       # keep the checked variant in step with the source

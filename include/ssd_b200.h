@@ -166,6 +166,21 @@ int ssd_incentive(const int64_t* actions_inc, const float* reward, int64_t rows,
                   float incentive, float cost, float ratio, int32_t max_seq_length,
                   float* rewards_for_env, float* rewards_for_inc, float* recv_sign, void* stream);
 
+/* ---- policy side of the rollout loop ------------------------------------------------- */
+
+/* EpsilonGreedyActionSelector.select_action (src/components/action_selectors.py:44-68) on the device.
+ * q [rows][n_actions] f32; avail [rows][n_actions] i32 0/1 or NULL (everything available); picked [rows] i64.
+ *   greedy      = first index of max over q with unavailable actions at -inf          (lines 57-58, 67)
+ *   pick_random = u_pick[row] < epsilon                                                (lines 62-64)
+ *   random      = the floor(u_act[row] * #available)-th available action               (line 66: multinomial over the mask)
+ * u_pick / u_act: injected uniforms in [0,1) (both or neither); NULL -> Philox4x32-10 keyed (seed; row, counter).
+ * The caller evaluates the epsilon schedule (epsilon_schedules.py) and passes 0 in test mode. */
+int ssd_select_actions(const float* q, const int32_t* avail, int64_t rows, int32_t n_actions, float epsilon,
+                       const float* u_pick, const float* u_act, uint64_t seed, uint64_t counter,
+                       int64_t* picked, void* stream);
+/* CUDA error of the most recent failing policy-side call on this thread. */
+int ssd_policy_last_cuda_error(void);
+
 /* Kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t ssd_launch_count(const ssd_handle* h);
 

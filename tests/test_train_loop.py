@@ -89,7 +89,8 @@ def test_run_sequential_cleanup3_end_to_end_on_the_cuda_env():
               "collective_return_mean", "equality_metric_mean", "ep_length_mean", "clean_num_mean", "apple_den_mean"):
         assert k in st and np.isfinite(st[k]), k
     assert st["ep_length_mean"] == 100.0
-    assert r["logger"].stats["episode"][-1][0] >= 2500          # t_env reached t_max
+    t_logged, episodes = r["logger"].stats["episode"][-1]      # logged every 1000 env steps (run.py:236-240)
+    assert t_logged >= 2000 and episodes >= 20
     print("run_sequential on the CUDA env: %.1f env-steps/s" % (2600 / r["seconds"]))
 
 
