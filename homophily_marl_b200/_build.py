@@ -12,7 +12,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 SRC = os.path.join(PKG_DIR, "csrc", "ssd_b200.cu")
-SRCS = [SRC, os.path.join(PKG_DIR, "csrc", "policy_b200.cu")]
+SRCS = [SRC, os.path.join(PKG_DIR, "csrc", "policy_b200.cu"), os.path.join(PKG_DIR, "csrc", "frontend_b200.cu")]
 HDR = os.path.join(ROOT, "include", "ssd_b200.h")
 LIB = os.path.join(PKG_DIR, "libssd_b200.so")
 

@@ -63,6 +63,12 @@ class BatchedEpisodeRunner:
         self.new_batch = partial(batch_cls, scheme, groups, self.batch_size, self.episode_limit + 1,
                                  preprocess=preprocess, device=self.args.device)
         self.mac = mac
+        # args.fused_frontend: during rollouts the MAC's rgb_preprocess (conv3x3 + FC on fp32 obs, homophily_controller.py:132-136)
+        # is served by the fused u8 front-end kernel reading the env's observation buffer (frontend.MacFrontEnd)
+        self.front = None
+        if getattr(self.args, "fused_frontend", False) and getattr(self.args, "rgb_input", False):
+            from .frontend import MacFrontEnd
+            self.front = MacFrontEnd(mac, self.env)
 
     def use_batch_factory(self, new_batch):
         """``new_batch()`` must return a fresh reference ``EpisodeBatch`` for B episodes of T+1 steps."""
@@ -94,6 +100,15 @@ class BatchedEpisodeRunner:
                 "agent_orientation": self._orient_vec[e.agent_orient.long()]}
 
     def run(self, test_mode=False):
+        if getattr(self, "front", None) is not None:
+            self.front.active = True
+        try:
+            return self._run(test_mode)
+        finally:
+            if getattr(self, "front", None) is not None:
+                self.front.active = False
+
+    def _run(self, test_mode=False):
         self.reset()
         e, B = self.env, self.batch_size
         terminated = False

@@ -1,0 +1,431 @@
+// frontend_b200.cu -- fused observation front end of the agent Q-network, sm_100a.
+//
+// Replaces, for rollouts, HomophilyAgent.rgb_preprocess = conv_to_fc (src/modules/agents/homophily_agent.py:19-27, called
+// from src/controllers/homophily_controller.py:132-136):
+//     u8 obs (env's padded plane layout)  ->  /256  ->  Conv2d(3, 6, k=3, s=1) + LeakyReLU  ->  Flatten
+//                                         ->  Linear(6 (N-2)^2, 32) + LeakyReLU              ->  f32 [rows][32]
+// so the fp32 observation (3.4x the bytes the env kernel just wrote) never exists.
+//
+// One persistent CTA per SM works on tiles of 128 agent views (GEMM rows):
+//   * warps 0-7  PRODUCERS: conv3x3 + LeakyReLU on the CUDA cores, straight from the u8 planes (27 aligned 32-bit loads give
+//                a 3x3x10 byte patch; 6 output channels x 8 pixels = 1296 FMAs per patch; conv weights come from the
+//                constant bank as FFMA operands).  The activations are the A operand of the FC contraction: each thread
+//                writes its 8 values of one output channel, split as tf32 hi + lo, into the K-major core-matrix layout the
+//                tensor core reads (no swizzle: 8 rows x 16 B cores, LBO 128 B, SBO 512 B);
+//   * warp 9     TMA: the FC weight tile of the stage ([32 x 16] hi + lo, pre-packed on the host in the same core-matrix
+//                layout) arrives with one cp.async.bulk.tensor.2d (SASS UTMALDG) on the stage's full-barrier;
+//   * warp 8     MMA: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=32, K=8), 16 accumulators in TMEM (512 columns);
+//   * warps 0-3  EPILOGUE after the last stage of a tile: tcgen05.ld (SASS LDTM) -> + bias -> LeakyReLU -> 128-bit stores.
+// A stage is one (pixel row y, 16-pixel block, output channel): A 128 x 16 (hi, lo: 16 KB) + B 32 x 16 (hi, lo: 4 KB); six
+// stages are in flight, so the conv of the next channels overlaps the contraction of the previous ones.
+//
+// Precision: the reference computes in fp32.  tf32 operands keep 10 mantissa bits, so both operands are split a = hi + lo
+// with hi = rn_tf32(a) and lo = rn_tf32(a - hi) (a - hi is exact in fp32, |lo| <= 2^-11 |a|), and the contraction is
+// hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM; the dropped lo*lo term and the rounding of lo are below 2^-21 relative
+// per product.  What dominates instead is the tensor core's own accumulation: adding a K=8 product sum to the running fp32
+// accumulator truncates, and the error grows linearly with the number of MMAs chained on one accumulator (measured: 4e-6
+// relative at 468 chained MMAs, 1.5e-5 at 2088).  Hence 16 accumulators: the hi*hi steps rotate over 15 of them, the lo terms
+// get their own, and the epilogue adds the partial sums in fp32.  tests/test_gpu_frontend.py states the tolerance against
+// torch fp32 and fp64.
+//
+// K is permuted (we own the packed weight format): k' = ((y * XB + xb) * 6 + oc) * 16 + px  <->  reference flatten index
+// k = oc * P^2 + y * P + 16 xb + px  (P = N - 2; pixels beyond P are padding: zero weights, zero activations).
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "ssd_b200.h"
+
+namespace {
+
+constexpr int kOC = 6;                       // conv_out   (config/default.yaml: conv_out 6, conv_kernel 3, conv_stride 1)
+constexpr int kFeat = 32;                    // obs_dim_net
+constexpr int kTileM = 128;                  // agent views per tile
+constexpr int kStageK = 16;                  // k' per stage: one output channel x 16 pixels
+constexpr int kStages = 6;
+constexpr int kABytes = kTileM * kStageK * 4;          // 8 KB (one of hi / lo)
+constexpr int kBBytes = kFeat * kStageK * 4;           // 2 KB (one of hi / lo)
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes; // 20 KB
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = kProducerThreads + 64;        // + MMA warp + TMA warp
+constexpr int kAccs = 16;                                // independent fp32 accumulators in TMEM (see `Precision`)
+constexpr uint32_t kTmemCols = kAccs * kFeat;          // 512 columns: the whole TMEM of the SM (one CTA per SM)
+
+struct FrontParams {
+    float conv_w[kOC * 27];                  // [oc][ch][dy][dx], pre-scaled by 1/256 (exact): the conv sees raw bytes
+    float conv_b[kOC];
+    float fc_b[kFeat];
+    float slope;
+    int N, P, RP, PS, AS, XB, n_chunks;      // obs geometry; chunks per tile = P * XB
+    long long rows;
+    int n_tiles;
+    const uint8_t* obs;
+    float* out;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = distance between the two cores of one K=8 step,
+// SBO = distance between 8-row groups (cute/arch/mma_sm100_desc.hpp SmemDescriptor, version 1 = Blackwell).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ CUtensorMap wmap) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_tmem_full, bar_tmem_empty;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), kProducerThreads + 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_tmem_full), 1);
+        mbar_init(smem_u32(&bar_tmem_empty), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {                                           // one warp allocates the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t smem_base = smem_u32(smem);
+    const int stages_per_tile = p.n_chunks * kOC;
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers (+ epilogue on warps 0-3)
+        const int r = tid & 127, strip = tid >> 7;             // GEMM row within the tile; 8-pixel half of the 16-pixel block
+        uint32_t it = 0, tile_n = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_n) {
+            const long long row = (long long)tile * kTileM + r;
+            const long long row_ld = row < p.rows ? row : p.rows - 1;          // partial last tile: compute on a valid row, never store
+            const uint8_t* view = p.obs + row_ld * p.AS;
+            for (int c = 0; c < p.n_chunks; ++c) {
+                const int y = c / p.XB, xb = c - y * p.XB;
+                const int x0 = xb * 16 + strip * 8;
+                // patch[ch][dy][0..9] as floats: raw bytes (the 1/256 lives in the conv weights)
+                float patch[3][3][10];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint8_t* src = view + ch * p.PS + (y + dy) * p.RP + x0;
+                        uint32_t w0 = 0, w1 = 0, w2 = 0;
+                        if (x0 < p.RP) w0 = __ldg(reinterpret_cast<const uint32_t*>(src));
+                        if (x0 + 4 < p.RP) w1 = __ldg(reinterpret_cast<const uint32_t*>(src + 4));
+                        if (x0 + 8 < p.N) w2 = __ldg(reinterpret_cast<const uint32_t*>(src + 8));   // only pixels x0+8, x0+9 < N are used
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            patch[ch][dy][b] = (float)((w0 >> (8 * b)) & 0xffu);
+                            patch[ch][dy][4 + b] = (float)((w1 >> (8 * b)) & 0xffu);
+                        }
+                        patch[ch][dy][8] = (float)(w2 & 0xffu);
+                        patch[ch][dy][9] = (float)((w2 >> 8) & 0xffu);
+                    }
+#pragma unroll
+                for (int oc = 0; oc < kOC; ++oc, ++it) {
+                    float acc[8];
+#pragma unroll
+                    for (int px = 0; px < 8; ++px) acc[px] = p.conv_b[oc];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const float w = p.conv_w[oc * 27 + ch * 9 + dy * 3 + dx];
+#pragma unroll
+                                for (int px = 0; px < 8; ++px) acc[px] = fmaf(w, patch[ch][dy][px + dx], acc[px]);
+                            }
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int px = 0; px < 8; ++px) {
+                        float a = leaky(acc[px], p.slope);
+                        if (x0 + px >= p.P) a = 0.f;                          // padding pixel of the 16-pixel block
+                        hi[px] = to_tf32(a);                                   // round-to-nearest tf32: exactly what the tensor core will read
+                        lo[px] = to_tf32(a - __uint_as_float(hi[px]));         // a - hi is exact in fp32; |lo| <= 2^-11 |a|
+                    }
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);               // the MMAs that read this slot have completed
+                    uint8_t* a_hi = smem + s * kStageBytes + (r >> 3) * 512 + (r & 7) * 16 + strip * 256;
+                    uint8_t* a_lo = a_hi + kABytes;
+                    *reinterpret_cast<uint4*>(a_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(a_hi + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(a_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(a_lo + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> tensor-core reads
+                    mbar_arrive(smem_u32(&bar_full[s]));
+                }
+            }
+            if (warp < 4) {
+                // -------------------------------------------------------------- epilogue: TMEM lane = GEMM row = r
+                mbar_wait(smem_u32(&bar_tmem_full), tile_n & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float sum[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+                // the partial sums are added smallest first (accumulator 0 holds the lo terms), in fp32 round-to-nearest
+                const int n_acc = min(kAccs, 1 + stages_per_tile * (kStageK / 8));   // tiny views use fewer than 16
+                for (int a = 0; a < n_acc; ++a) {
+                    uint32_t v[32];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                 : "r"(taddr + (uint32_t)(a * kFeat)) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(smem_u32(&bar_tmem_empty));                        // the accumulator may be overwritten by the next tile
+                if (row < p.rows) {
+                    float4* dst = reinterpret_cast<float4*>(p.out + row * kFeat);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o;
+                        o.x = leaky(sum[4 * j + 0] + p.fc_b[4 * j + 0], p.slope);
+                        o.y = leaky(sum[4 * j + 1] + p.fc_b[4 * j + 1], p.slope);
+                        o.z = leaky(sum[4 * j + 2] + p.fc_b[4 * j + 2], p.slope);
+                        o.w = leaky(sum[4 * j + 3] + p.fc_b[4 * j + 3], p.slope);
+                        dst[j] = o;
+                    }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ---------------------------------------------------------------------- MMA issuer (one elected lane)
+        // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 32, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kFeat >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        uint32_t it = 0, tile_n = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_n) {
+            if (tile_n > 0) mbar_wait(smem_u32(&bar_tmem_empty), (tile_n - 1) & 1u);   // the epilogue has drained the previous tile
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t used = 0;                                                 // accumulators already written in this tile
+            for (int st = 0; st < stages_per_tile; ++st, ++it) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                mbar_wait(smem_u32(&bar_full[s]), ph);                         // A written by 256 producers, B landed by TMA
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_base + s * kStageBytes, a_lo = a_hi + kABytes;
+                    const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + kBBytes;
+#pragma unroll
+                    for (int ks = 0; ks < kStageK / 8; ++ks) {                 // one K=8 step = two 16-byte cores, 256 B further on
+                        const uint64_t dah = umma_desc(a_hi + ks * 256, 128, 512), dal = umma_desc(a_lo + ks * 256, 128, 512);
+                        const uint64_t dbh = umma_desc(b_hi + ks * 256, 128, 512), dbl = umma_desc(b_lo + ks * 256, 128, 512);
+                        // the tensor core truncates when it aligns a product sum with the running accumulator, so the error
+                        // grows with the number of MMAs chained on one accumulator: the hi*hi steps rotate over 15
+                        // accumulators, the (2^-11 smaller) lo terms have their own; the epilogue adds the 16 partial sums
+                        const uint32_t acc = 1u + (uint32_t)(st * (kStageK / 8) + ks) % (kAccs - 1);
+                        umma_tf32(tmem_base + acc * kFeat, dah, dbh, idesc, (used >> acc) & 1u);
+                        umma_tf32(tmem_base, dal, dbh, idesc, used & 1u);
+                        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                        used |= 1u | (1u << acc);
+                    }
+                    umma_commit(smem_u32(&bar_empty[s]));                      // frees the slot when these MMAs have read it
+                    if (st == stages_per_tile - 1) umma_commit(smem_u32(&bar_tmem_full));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------- TMA: FC weight tile of every stage
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+                for (int st = 0; st < stages_per_tile; ++st, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    mbar_arrive_expect_tx(full, 2 * kBBytes);
+                    tma_load_2d(smem_base + s * kStageBytes + 2 * kABytes, &wmap, full, 0, st * 4);   // 4 rows of 256 floats = hi + lo
+                }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(kTmemCols) : "memory");
+}
+
+thread_local int g_front_cuda_error = 0;
+
+inline float host_tf32(float v) {                              // cvt.rna.tf32.f32: nearest, ties away from zero (finite inputs)
+    uint32_t bits; memcpy(&bits, &v, 4);
+    bits = (bits + 0x1000u) & 0xffffe000u;
+    float r; memcpy(&r, &bits, 4);
+    return r;
+}
+
+}  // namespace
+
+struct ssd_frontend {
+    FrontParams fp;
+    CUtensorMap wmap;
+    float* d_w;                                                // packed FC weights: [stages][hi 512 | lo 512] floats
+    int device, view, sms;
+    size_t smem_bytes;
+};
+
+extern "C" {
+
+int ssd_frontend_create(int32_t view, const float* conv_w, const float* conv_b, const float* fc_w, const float* fc_b,
+                        float negative_slope, int32_t device, ssd_frontend** out) {
+    if (!out) return SSD_ERR_INVALID;
+    *out = nullptr;
+    if (!conv_w || !conv_b || !fc_w || !fc_b || view < 1 || view > 31) return SSD_ERR_INVALID;
+    const int N = 2 * view + 1, P = N - 2, XB = (P + 15) / 16, n_chunks = P * XB, stages = n_chunks * kOC;
+    ssd_frontend* f = new (std::nothrow) ssd_frontend;
+    if (!f) return SSD_ERR_INVALID;
+    memset(f, 0, sizeof(*f));
+    FrontParams& p = f->fp;
+    for (int i = 0; i < kOC * 27; ++i) p.conv_w[i] = conv_w[i] * (1.0f / 256.0f);    // exact: get_obs() = u8 / 256 (map_env.py:943)
+    for (int i = 0; i < kOC; ++i) p.conv_b[i] = conv_b[i];
+    for (int i = 0; i < kFeat; ++i) p.fc_b[i] = fc_b[i];
+    p.slope = negative_slope; p.N = N; p.P = P; p.XB = XB; p.n_chunks = n_chunks;
+    f->view = view; f->device = device;
+
+    // FC weights, permuted to k' and laid out per stage exactly as the shared-memory image the tensor core reads:
+    // element (n, kk) of a [32 x 16] tile at float offset (n/8)*128 + (kk/4)*32 + (n%8)*4 + kk%4 ; hi image then lo image.
+    std::vector<float> packed((size_t)stages * 1024, 0.f);
+    for (int st = 0; st < stages; ++st) {
+        const int c = st / kOC, oc = st % kOC, y = c / XB, xb = c % XB;
+        for (int n = 0; n < kFeat; ++n)
+            for (int kk = 0; kk < kStageK; ++kk) {
+                const int x = xb * 16 + kk;
+                if (x >= P) continue;
+                const float w = fc_w[(size_t)n * (kOC * P * P) + (size_t)oc * P * P + y * P + x];   // nn.Linear.weight [32][6 P^2], Flatten order (oc, y, x)
+                const float hi = host_tf32(w);
+                const size_t off = (size_t)st * 1024 + (n / 8) * 128 + (kk / 4) * 32 + (n % 8) * 4 + kk % 4;
+                packed[off] = hi;
+                packed[off + 512] = host_tf32(w - hi);
+            }
+    }
+    int prev = -1;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e == cudaSuccess && prev != device) e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_w, packed.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&f->sms, cudaDevAttrMultiProcessorCount, device);
+    int rc = SSD_OK;
+    if (e == cudaSuccess) {
+        // rank-2 tensor map over the packed weights viewed as [stages * 4][256] f32; box = 4 rows x 256 = one stage (4 KB)
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && (!fn || qres != cudaDriverEntryPointSuccess)) rc = SSD_ERR_CUDA;
+        if (e == cudaSuccess && rc == SSD_OK) {
+            const cuuint64_t dims[2] = { 256, (cuuint64_t)stages * 4 };
+            const cuuint64_t strides[1] = { 1024 };
+            const cuuint32_t box[2] = { 256, 4 };
+            const cuuint32_t estr[2] = { 1, 1 };
+            const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&f->wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, f->d_w, dims, strides, box, estr,
+                                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) { g_front_cuda_error = (int)cr; rc = SSD_ERR_CUDA; }
+        }
+    }
+    f->smem_bytes = (size_t)kStages * kStageBytes + 1024;
+    if (e == cudaSuccess && rc == SSD_OK)
+        e = cudaFuncSetAttribute(obs_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_bytes);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess || rc != SSD_OK) {
+        if (e != cudaSuccess) g_front_cuda_error = (int)e;
+        if (f->d_w) cudaFree(f->d_w);
+        delete f;
+        return SSD_ERR_CUDA;
+    }
+    *out = f;
+    return SSD_OK;
+}
+
+int ssd_frontend_forward(ssd_frontend* f, const uint8_t* obs, int64_t rows, int32_t obs_agent_stride, int32_t obs_plane_stride,
+                         int32_t obs_row_stride, float* out, void* stream) {
+    if (!f || !obs || !out || rows < 0) return SSD_ERR_INVALID;
+    if (rows == 0) return SSD_OK;
+    FrontParams p = f->fp;
+    if (obs_row_stride < p.N || (obs_row_stride & 3) || obs_plane_stride < p.N * obs_row_stride || (obs_plane_stride & 3) ||
+        obs_agent_stride < 3 * obs_plane_stride || (obs_agent_stride & 3) || (reinterpret_cast<uintptr_t>(obs) & 3) ||
+        (reinterpret_cast<uintptr_t>(out) & 15))
+        return SSD_ERR_INVALID;
+    p.RP = obs_row_stride; p.PS = obs_plane_stride; p.AS = obs_agent_stride;
+    p.rows = rows; p.n_tiles = (int)((rows + kTileM - 1) / kTileM);
+    p.obs = obs; p.out = out;
+    int prev = -1;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e == cudaSuccess && prev != f->device) e = cudaSetDevice(f->device);
+    if (e == cudaSuccess) {
+        const int grid = p.n_tiles < f->sms ? p.n_tiles : f->sms;
+        obs_frontend_kernel<<<grid, kThreads, f->smem_bytes, (cudaStream_t)stream>>>(p, f->wmap);
+        e = cudaGetLastError();
+    }
+    if (prev >= 0 && prev != f->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) { g_front_cuda_error = (int)e; return SSD_ERR_CUDA; }
+    return SSD_OK;
+}
+
+int ssd_frontend_destroy(ssd_frontend* f) {
+    if (!f) return SSD_ERR_INVALID;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != f->device) cudaSetDevice(f->device);
+    cudaFree(f->d_w);
+    if (prev >= 0 && prev != f->device) cudaSetDevice(prev);
+    delete f;
+    return SSD_OK;
+}
+
+int ssd_frontend_last_cuda_error(void) { return g_front_cuda_error; }
+
+}  // extern "C"

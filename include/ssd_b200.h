@@ -181,6 +181,21 @@ int ssd_select_actions(const float* q, const int32_t* avail, int64_t rows, int32
 /* CUDA error of the most recent failing policy-side call on this thread. */
 int ssd_policy_last_cuda_error(void);
 
+/* Fused observation front end of the agent network: HomophilyAgent.rgb_preprocess == conv_to_fc
+ * (src/modules/agents/homophily_agent.py:19-27; call site src/controllers/homophily_controller.py:132-136) for rollouts:
+ *   u8 obs planes (the env's layout) -> /256 -> Conv2d(3,6,k3,s1)+LeakyReLU -> Flatten -> Linear(6(N-2)^2, 32)+LeakyReLU.
+ * conv on the CUDA cores, the Linear contraction on tcgen05 tensor cores (tf32 hi/lo split, fp32 accumulate in TMEM).
+ * conv_w [6][3][3][3], conv_b [6], fc_w [32][6(N-2)^2] (nn.Linear.weight, Flatten order), fc_b [32]: HOST pointers, copied.
+ * Shapes are the reference's defaults (config/default.yaml: conv_out 6, conv_kernel 3, conv_stride 1, obs_dim_net 32). */
+typedef struct ssd_frontend ssd_frontend;
+int ssd_frontend_create(int32_t view, const float* conv_w, const float* conv_b, const float* fc_w, const float* fc_b,
+                        float negative_slope, int32_t device, ssd_frontend** out);
+/* obs: DEVICE u8, `rows` agent views `obs_agent_stride` bytes apart (ssd_layout strides); out: DEVICE f32 [rows][32]. */
+int ssd_frontend_forward(ssd_frontend* f, const uint8_t* obs, int64_t rows, int32_t obs_agent_stride, int32_t obs_plane_stride,
+                         int32_t obs_row_stride, float* out, void* stream);
+int ssd_frontend_destroy(ssd_frontend* f);
+int ssd_frontend_last_cuda_error(void);
+
 /* Kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t ssd_launch_count(const ssd_handle* h);
 

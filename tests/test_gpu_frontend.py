@@ -1,0 +1,93 @@
+"""GPU suite: the fused u8-obs front end equals the reference module
+``nn.Sequential(Conv2d(3,6,3,1), LeakyReLU, Flatten, Linear(6(N-2)^2, 32), LeakyReLU)`` applied to ``obs / 256``
+(src/modules/agents/homophily_agent.py:19-27).
+
+Tolerance (stated, not hidden): the reference computes in fp32.  The kernel's conv is fp32 FMA; the Linear contraction runs
+on tf32 tensor cores with both operands split hi + lo (hi*hi + lo*hi + hi*lo, fp32 accumulate), which leaves a relative
+error below 2^-19 per product.  Against an fp64 evaluation of the same module the kernel must be within 4e-6 * (1 + |y|)
+-- the same order as torch's own fp32 error -- and within 1e-5 * (1 + |y|) of torch fp32 on the GPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _module(view, seed):
+    torch.manual_seed(seed)
+    P = 2 * view - 1
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 6, 3, 1), torch.nn.LeakyReLU(), torch.nn.Flatten(),
+                               torch.nn.Linear(6 * P * P, 32), torch.nn.LeakyReLU())
+
+
+def _compare(fe, mod, obs_buf, rows, lay, N):
+    dev = obs_buf.device
+    got = fe.forward(obs_buf, rows, lay["AS"], lay["PS"], lay["RP"])
+    view = obs_buf.as_strided((rows, 3, N, N), (lay["AS"], lay["PS"], lay["RP"], 1))
+    x32 = view.float() / 256
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want32 = mod.to(dev)(x32)
+            want64 = mod.to("cpu").double()(view.cpu().double() / 256)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        mod.float()
+    g, w32, w64 = got.cpu().double(), want32.cpu().double(), want64
+    err64 = ((g - w64).abs() / (1 + w64.abs())).max().item()
+    err32 = ((g - w32).abs() / (1 + w32.abs())).max().item()
+    torch_err64 = ((w32 - w64).abs() / (1 + w64.abs())).max().item()
+    assert err64 < 4e-6 and err32 < 1e-5, (err64, err32, torch_err64)
+    return err64, torch_err64
+
+
+@pytest.mark.parametrize("view,rows", [(7, 1), (7, 127), (7, 128), (7, 129), (7, 20480), (15, 5), (15, 300), (15, 20480), (3, 200), (1, 130)])
+def test_fused_front_end_matches_the_reference_module(view, rows):
+    from homophily_marl_b200.frontend import ObsFrontEnd
+    dev = torch.device("cuda:0")
+    N = 2 * view + 1
+    RP = (N + 3) // 4 * 4
+    PS, AS = N * RP, (3 * N * RP + 15) // 16 * 16
+    g = torch.Generator().manual_seed(view * 1000 + rows)
+    buf = torch.randint(0, 256, (rows * AS,), generator=g, dtype=torch.int32).to(torch.uint8).to(dev)     # pad bytes are garbage on purpose
+    mod = _module(view, seed=rows)
+    fe = ObsFrontEnd.from_module(mod, view, device=dev)
+    err, terr = _compare(fe, mod, buf, rows, dict(AS=AS, PS=PS, RP=RP), N)
+    print(f"view {view} rows {rows}: max rel err vs fp64 {err:.2e} (torch fp32: {terr:.2e})")
+    if rows >= 20480:                                          # informational timing: fused kernel vs the torch module on fp32 obs
+        def timed(fn, reps=20):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps * 1e3
+        mod.to(dev)
+        v4 = buf.as_strided((rows, 3, N, N), (AS, PS, RP, 1))
+        with torch.no_grad():
+            t_fused = timed(lambda: fe.forward(buf, rows, AS, PS, RP))
+            t_torch = timed(lambda: mod(v4.float() / 256))
+        print(f"view {view} rows {rows}: fused {t_fused:.1f} us, torch (u8->f32 /256 + conv + linear) {t_torch:.1f} us")
+    fe.close()
+
+
+@pytest.mark.parametrize("name,mp,n,view", [("cleanup", "default5", 5, 7), ("harvest", "default5", 5, 15)])
+def test_front_end_on_env_observations(name, mp, n, view):
+    """Straight from the env's observation buffer after real steps (the rollout call site)."""
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    from homophily_marl_b200.frontend import ObsFrontEnd
+    env = SSDBatchEnv(name, 300, n, map=mp, view_size=view, seed=4, extra_args=dict(random_spawn_point=True, random_spawn_rotation=None))
+    env.reset()
+    rs = np.random.RandomState(1)
+    for _ in range(5):
+        env.step(torch.as_tensor(rs.randint(0, env.n_actions, size=(300, n)).astype(np.uint8), device=env.device))
+    mod = _module(view, seed=11)
+    fe = ObsFrontEnd.from_module(mod, view, device=env.device)
+    lay = env.layout
+    _compare(fe, mod, env.obs_buf.view(-1), 300 * n, dict(AS=lay.obs_agent_stride, PS=lay.obs_plane_stride, RP=lay.obs_row_stride), env.N)
+    out = fe.forward_env(env)
+    assert out.shape == (300 * n, 32) and out.dtype == torch.float32

@@ -131,3 +131,44 @@ def test_run_sequential_with_the_batched_runner():
     for k in ("return_mean", "test_return_mean", "loss_value_env", "loss_value_inc", "loss_sim", "ep_length_mean"):
         assert k in st and np.isfinite(st[k]), k
     assert st["ep_length_mean"] == 100.0
+
+
+def test_batched_runner_with_fused_front_end_and_device_selector():
+    """f2 + f3 wired into the rollout: the MAC's rgb_preprocess is served by the tcgen05 front-end kernel from the env's u8
+    buffer and epsilon-greedy runs as one kernel; the module path stays in place for the learner (autograd)."""
+    B = 128
+    cfg = _cfg(runner="batched", batch_size_run=B, buffer_size=2 * B, batch_size=8, buffer_cpu_only=False, fused_frontend=True,
+               action_selector="epsilon_greedy_b200", test_nepisode=B, env_args=dict(num_agents=3, map="default3", episode_limit=20))
+    c = refloop.build_components(cfg, backend="b200")
+    from homophily_marl_b200.frontend import MacFrontEnd
+    from homophily_marl_b200.selectors import DeviceEpsilonGreedySelector
+    assert isinstance(c.runner.front, MacFrontEnd) and isinstance(c.mac.action_selector, DeviceEpsilonGreedySelector)
+    calls = {"fused": 0}
+    fwd = c.runner.front._front_end().forward_env
+
+    def counting(env, *a, **k):
+        calls["fused"] += 1
+        return fwd(env, *a, **k)
+    c.runner.front._front_end().forward_env = counting
+    batch = c.runner.run(test_mode=False)
+    assert calls["fused"] == 21 and bool(batch["filled"].all())               # one per select_actions_env call (T + 1)
+    # the fused features equal the module's on the stored fp32 observations (tolerance: tests/test_gpu_frontend.py)
+    t = 7
+    x = batch["obs"][:, t].reshape(B * 3, 3, 15, 15)
+    with torch.no_grad():
+        want = c.runner.front.original(x)
+    c.runner.env.obs_buf.zero_()
+    lay = c.runner.env.layout
+    u8 = (batch["obs"][:, t] * 256).to(torch.uint8)
+    c.runner.env.obs_view().copy_(u8)
+    got = c.runner.front._front_end().forward_env(c.runner.env)
+    assert torch.allclose(got, want, rtol=0, atol=1e-5 * (1 + want.abs().max().item()))
+    _oracle_replay(batch, c.runner.env.spec, seed=cfg["seed"])
+    c.buffer.insert_episode_batch(batch)
+    sample = c.buffer.sample(8)
+    c.learner.train(sample[:, :sample.max_t_filled()], c.runner.t_env, B)      # optimiser step -> parameter versions change
+    stamp = c.runner.front._stamp
+    c.runner.run(test_mode=True)
+    assert c.runner.front._stamp != stamp                                      # the weights were re-packed after the update
+    assert np.isfinite(c.logger.stats["loss_value_env"][-1][1])
+    c.runner.close_env()
