@@ -40,7 +40,7 @@ class SsdLayout(C.Structure):
 
 
 class SsdState(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("grid", "agent", "ep_ret", "t", "tick")]
+    _fields_ = [(k, C.c_void_p) for k in ("grid", "agent", "ep_ret", "t", "tick", "counts")]
 
 
 class SsdStepOut(C.Structure):

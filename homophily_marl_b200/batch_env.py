@@ -87,6 +87,7 @@ class SSDBatchEnv:
         self.ep_ret_buf = z((B, lay.agent_stride), torch.int32)
         self.t_buf = z((B,), torch.int32)
         self.tick_buf = z((B,), torch.int32)
+        self.counts_buf = z((B,), torch.int32)                 # #apple cells | #waste cells << 16 of every grid
         self.reward = z((B, n), torch.int8)
         self.clean = z((B, n), torch.uint8)
         self.apple_cnt = z((B,), torch.int16)
@@ -94,7 +95,7 @@ class SSDBatchEnv:
         self.obs_buf = self.new_obs_buffer()
         self.state_rgb = z((B, 3, self.H, self.W), torch.uint8) if want_state else None
         self._st = _capi.SsdState(*[t.data_ptr() for t in (self.grid_buf, self.agent_buf, self.ep_ret_buf,
-                                                            self.t_buf, self.tick_buf)])
+                                                            self.t_buf, self.tick_buf, self.counts_buf)])
         self._keep = None
 
     # ------------------------------------------------------------------ buffers / views
@@ -132,6 +133,7 @@ class SSDBatchEnv:
         if grid is not None:
             g = torch.as_tensor(np.asarray(grid, dtype=np.uint8).reshape(-1), device=self.device)
             self.grid_buf[b, :self.G] = g
+            self._recount(slice(b, b + 1))
         if pos_rc is not None or orient is not None:
             a = self.agent_buf[b, :self.n].cpu().numpy().astype(np.int64)
             if pos_rc is not None:
@@ -141,11 +143,17 @@ class SSDBatchEnv:
                 a = (a & 0xFFFF) | (np.asarray(orient, dtype=np.int64) << 16)
             self.agent_buf[b, :self.n] = torch.as_tensor(a.astype(np.int32), device=self.device)
 
+    def _recount(self, sel):
+        """ssd_state.counts of the selected envs from their grids (needed after writing a grid directly)."""
+        g = self.grid_buf[sel, :self.G]
+        self.counts_buf[sel] = ((g == 2).sum(1) | ((g == 3).sum(1) << 16)).to(torch.int32)
+
     def load_state(self, grid=None, pos_rc=None, orient=None, t=None):
         """Batched variant of ``set_state``: NumPy arrays [B,H,W] / [B,n,2] / [B,n] / [B]."""
         if grid is not None:
             g = np.ascontiguousarray(grid, dtype=np.uint8).reshape(self.B, self.G)
             self.grid_buf[:, :self.G] = torch.as_tensor(g, device=self.device)
+            self._recount(slice(None))
         if pos_rc is not None or orient is not None:
             a = self.agent_buf[:, :self.n].cpu().numpy().astype(np.int64)
             if pos_rc is not None:

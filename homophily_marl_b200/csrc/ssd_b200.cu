@@ -70,6 +70,7 @@ struct KParams {
     int episode_limit, fire_cost, hit_penalty, beam_len, n_actions;
     int n_apple, n_waste, n_spawn, n_apple4, n_waste2;
     int random_spawn, spawn_rot;
+    int base_apples, base_waste;              // 'A' / 'H' cells of the reset grid (cell counts are carried in ssd_state.counts)
     int smem_per_warp, off_pmap;
     uint32_t invN20, invW20, invMW20, invMTW20;   // floor(x / d) == (x * inv) >> 20 on the used ranges
     uint32_t seed_lo, seed_hi, gid_base;
@@ -77,7 +78,7 @@ struct KParams {
     uint32_t lut[16];
     uint32_t lut8[6];                         // 8-entry colour LUT per plane (lo, hi words): R, G, B
     const MapDev* map;
-    uint8_t* grid; uint32_t* agent; int32_t* ep_ret; int32_t* t; uint32_t* tick;
+    uint8_t* grid; uint32_t* agent; int32_t* ep_ret; int32_t* t; uint32_t* tick; uint32_t* counts;
     const uint8_t* actions; const uint8_t* mask;
     int8_t* reward; uint8_t* clean; uint16_t* apple_cnt; uint8_t* done; uint8_t* obs; uint8_t* state_rgb;
     const uint32_t* d_prio; const uint32_t* d_uapple; const uint32_t* d_uwaste; const uint32_t* d_wkey;
@@ -132,12 +133,10 @@ struct GeoS {                                                 // compile-time ge
     __device__ __forceinline__ int pitchT() const { return v.pitchT; }
     __device__ __forceinline__ int PMS() const { return v.PMS; }
     __device__ __forceinline__ uint32_t maskM8() const { return v.maskM8; }
-    __device__ __forceinline__ uint32_t maskT8() const { return v.maskT8; }
     __device__ __forceinline__ int off_map(int o) const { return o == 0 ? v.off0 : (o == 1 ? v.off1 : (o == 2 ? v.off2 : v.off3)); }
     __device__ __forceinline__ int divW(int x) const { return (int)((unsigned)x / (unsigned)v.W); }
     __device__ __forceinline__ int divN(int x) const { return (int)((unsigned)x / (unsigned)v.N); }
     __device__ __forceinline__ int divMW(int x) const { return (int)((unsigned)x / (unsigned)v.nw8M); }
-    __device__ __forceinline__ int divMTW(int x) const { return (int)((unsigned)x / (unsigned)v.nw8T); }
 };
 
 struct GeoD {                                                 // runtime geometry (any wall-enclosed map)
@@ -160,12 +159,10 @@ struct GeoD {                                                 // runtime geometr
     __device__ __forceinline__ int pitchT() const { return p.pitchT; }
     __device__ __forceinline__ int PMS() const { return p.PMS; }
     __device__ __forceinline__ uint32_t maskM8() const { return p.maskM8; }
-    __device__ __forceinline__ uint32_t maskT8() const { return p.maskT8; }
     __device__ __forceinline__ int off_map(int o) const { return p.off_map[o]; }
     __device__ __forceinline__ int divW(int x) const { return (int)(((uint32_t)x * p.invW20) >> 20); }
     __device__ __forceinline__ int divN(int x) const { return (int)(((uint32_t)x * p.invN20) >> 20); }
     __device__ __forceinline__ int divMW(int x) const { return (int)(((uint32_t)x * p.invMW20) >> 20); }
-    __device__ __forceinline__ int divMTW(int x) const { return (int)(((uint32_t)x * p.invMTW20) >> 20); }
 };
 
 // ------------------------------------------------------------------ Philox4x32-10
@@ -211,15 +208,6 @@ __device__ __forceinline__ void warp_for(int n, int lane, F f) {
     int i = lane;
     if (i < n) f(i);
     for (i += STRIDE; i < n; i += STRIDE) f(i);
-}
-// bit 7 of every byte of w that differs from the corresponding byte of pat (exact, no cross-byte borrow)
-__device__ __forceinline__ uint32_t ne_bytes(uint32_t w, uint32_t pat) {
-    const uint32_t t = w ^ pat;
-    return (((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;
-}
-__device__ __forceinline__ int count_eq16(const uint4& v, uint32_t pat) {      // bytes of a 16-byte vector equal to pat's byte
-    const uint32_t m = (ne_bytes(v.x, pat) >> 7) | (ne_bytes(v.y, pat) >> 6) | (ne_bytes(v.z, pat) >> 5) | (ne_bytes(v.w, pat) >> 4);
-    return 16 - __popc(m);
 }
 // draw streams: 0 mover priority, 1 apple, 2 waste (u, order key), 3 spawn key, 4 spawn rotation
 __device__ __forceinline__ uint32_t philox_word(const KParams& p, uint32_t gid, uint32_t tick, uint32_t stream, uint32_t idx) {
@@ -333,7 +321,7 @@ constexpr uint8_t kOcc = 0x80;
 // ------------------------------------------------------------------ beams (map_env.py:663-769)
 template <class SW, class GEO>
 __device__ __forceinline__ void beams(const SW& w, const GEO& g, const KParams& p, uint8_t* sg, int lane, bool is_agent,
-                                      int act, int pos, int ori, int& reward, int& clean_num) {
+                                      int act, int pos, int ori, int& reward, int& clean_num, int& waste) {
     const bool fire = is_agent && act == 7;
     const bool clean = is_agent && act == 8 && g.kind() == SSD_KIND_CLEANUP;
     if (fire) reward -= p.fire_cost;                          // agent.py:188-190, 239-241
@@ -368,6 +356,7 @@ __device__ __forceinline__ void beams(const SW& w, const GEO& g, const KParams& 
         w.sync();
         const unsigned um = w.ballot(upd >= 0);
         if (lane == i && is_clean) clean_num = __popc(um);    // 672-673
+        waste -= __popc(um);                                  // only CLEAN produces updates: 'H' -> 'R'
         if (p.hit_penalty != 0) {                             // hit(): the LAST index standing on the cell (agent.py:184-186)
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
@@ -380,27 +369,17 @@ __device__ __forceinline__ void beams(const SW& w, const GEO& g, const KParams& 
 }
 
 // ------------------------------------------------------------------ spawning (cleanup.py:165-204, harvest.py:92-122)
+// `apples` / `waste` are the env's running cell counts (ssd_state.counts): the reference recounts the map every step
+// (map_env.py:291-292, cleanup.py:206-212); here consume / clean / spawn keep them up to date, which is the same number.
 template <class SW, class GEO>
-__device__ __forceinline__ int spawn(const SW& w, const GEO& g, const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick) {
+__device__ __forceinline__ void spawn(const SW& w, const GEO& g, const KParams& p, uint8_t* sg, int lane, int env, uint32_t gid, uint32_t tick,
+                                      int& apples, int& waste) {
     const MapDev* __restrict__ m = p.map;
     uint32_t tA = 1, tW = 0;
-    // one pass over the staged grid: apples (density numerator, map_env.py:291-292; none lies under an agent after
-    // consume) in the high half, Cleanup's waste count (compute_permitted_area, occupancy bit ignored) in the low half
-    int acc = 0;
-    warp_for<SW::kLanes>(g.GS() >> 4, lane, [&](int i) {
-        uint4 v = reinterpret_cast<const uint4*>(sg)[i];
-        acc += count_eq16(v, 0x02020202u) << 16;
-        if (g.kind() == SSD_KIND_CLEANUP) {
-            v.x &= 0x7f7f7f7fu; v.y &= 0x7f7f7f7fu; v.z &= 0x7f7f7f7fu; v.w &= 0x7f7f7f7fu;
-            acc += count_eq16(v, 0x03030303u);
-        }
-    });
-    acc = w.radd(acc);
-    int apples = acc >> 16;
     if (g.kind() == SSD_KIND_CLEANUP) {
-        const int h = acc & 0xffff;
-        tA = __ldg(&m->thr_apple[h]);
-        tW = __ldg(&m->thr_waste[h]);
+        SSD_CHECK(waste >= 0 && waste <= p.n_waste);
+        tA = __ldg(&m->thr_apple[waste]);
+        tW = __ldg(&m->thr_waste[waste]);
     }
     // apples: 4 candidate points per lane per Philox call; decisions use the pre-spawn grid
     unsigned long long decided = 0;
@@ -469,7 +448,7 @@ __device__ __forceinline__ int spawn(const SW& w, const GEO& g, const KParams& p
     if (wcell >= 0 && lane == 0) sg[wcell] = (uint8_t)(SSD_CELL_WASTE | (sg[wcell] & kOcc));
     w.sync();
     if (w.ballot(decided != 0)) apples += w.radd(__popcll(decided));
-    return apples;
+    waste += wcell >= 0;
 }
 
 // ------------------------------------------------------------------ render (map_env.py:360-379, 418-446, 795-815, 923-957)
@@ -616,21 +595,44 @@ __device__ __forceinline__ void build_rowmap(const SW& w, const GEO& g, const KP
         *reinterpret_cast<uint32_t*>(map + (r + g.V()) * g.pitchM() + (g.LPn() >> 1) + 4 * j) = w;
     }
 }
-// Transposed map: source strided by W.
+// Transposed map from M: one lane transposes one 8 x 8 block of nibbles (8 words in, 8 words out) with three butterfly
+// stages (swap 1-, 2-, 4-nibble sub-blocks across the diagonal).  Rows below the map come from M's first padding row and
+// columns right of the map from M's tail nibbles, both "outside", which is exactly what MT's own padding holds.
 template <class SW, class GEO>
-__device__ __forceinline__ void build_colmap(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* map, int lane) {
-    const int total = g.W() * g.nw8T();
-#pragma unroll 4
-    for (int i = lane; i < total; i += SW::kLanes) {
-        const int c = g.divMTW(i), j = i - c * g.nw8T();
-        uint32_t b[8];
+__device__ __forceinline__ void build_colmap(const SW& w, const GEO& g, const KParams& p, const uint8_t* M, uint8_t* MT, int lane) {
+    const int total = g.nw8T() * g.nw8M();
+    for (int blk = lane; blk < total; blk += SW::kLanes) {
+        const int i = g.divMW(blk), j = blk - i * g.nw8M();   // rows 8i.., columns 8j..
+        uint32_t a[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) b[k] = sg[min(8 * j + k, g.H() - 1) * g.W() + c];   // rows past the map: clamped, masked below
-        const uint32_t y0 = b[0] | (b[1] << 4), y1 = b[2] | (b[3] << 4), y2 = b[4] | (b[5] << 4), y3 = b[6] | (b[7] << 4);
-        uint32_t w = prmt(prmt(y0, y1, 0x0040), prmt(y2, y3, 0x0040), 0x5410);
-        if (j == g.nw8T() - 1) w = (w & g.maskT8()) | (0x66666666u & ~g.maskT8());
-        SSD_CHECK((c + g.V()) * g.pitchT() + (g.LPn() >> 1) + 4 * j + 4 <= (g.W() + 2 * g.V()) * g.pitchT());
-        *reinterpret_cast<uint32_t*>(map + (c + g.V()) * g.pitchT() + (g.LPn() >> 1) + 4 * j) = w;
+        for (int k = 0; k < 8; ++k) {
+            const int r = min(8 * i + k, g.H());              // H = first bottom padding row of M
+            SSD_CHECK((r + g.V()) * g.pitchM() + (g.LPn() >> 1) + 4 * j + 4 <= (g.H() + 2 * g.V()) * g.pitchM());
+            a[k] = *reinterpret_cast<const uint32_t*>(M + (r + g.V()) * g.pitchM() + (g.LPn() >> 1) + 4 * j);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {                      // 1-nibble sub-blocks
+            const uint32_t t = ((a[k] >> 4) ^ a[k + 1]) & 0x0f0f0f0fu;
+            a[k + 1] ^= t; a[k] ^= t << 4;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (!(k & 2)) {           // 2-nibble sub-blocks
+            const uint32_t t = ((a[k] >> 8) ^ a[k + 2]) & 0x00ff00ffu;
+            a[k + 2] ^= t; a[k] ^= t << 8;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                         // 4-nibble sub-blocks
+            const uint32_t t = ((a[k] >> 16) ^ a[k + 4]) & 0x0000ffffu;
+            a[k + 4] ^= t; a[k] ^= t << 16;
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int c = 8 * j + x;
+            if (c < g.W()) {
+                SSD_CHECK((c + g.V()) * g.pitchT() + (g.LPn() >> 1) + 4 * i + 4 <= (g.W() + 2 * g.V()) * g.pitchT());
+                *reinterpret_cast<uint32_t*>(MT + (c + g.V()) * g.pitchT() + (g.LPn() >> 1) + 4 * i) = a[x];
+            }
+        }
     }
 }
 
@@ -677,19 +679,21 @@ __device__ __forceinline__ void render(const SW& w, const GEO& g, const KParams&
     const uint32_t abase_sh = (uint32_t)(g.off_map(ori) + (rowc + (down ? 2 * g.V() : 0)) * pitch + ((s >> 3) << 2))
                               | ((uint32_t)((rev ? 7 - (s & 7) : (s & 7)) * 4) << 16) | ((uint32_t)rev << 24);
     const int astep = down ? -pitch : pitch;
-    const bool needT = w.ballot(is_agent && ori < 2) != 0, needM = w.ballot(is_agent && ori >= 2) != 0;
+    const bool needT = w.ballot(is_agent && ori < 2) != 0;
     w.sync();
     uint8_t* MT = pmap + g.off_map(0);
     uint8_t* M = pmap + g.off_map(2);
-    if (needM) build_rowmap(w, g, p, sg, M, lane);
-    if (needT) build_colmap(w, g, p, sg, MT, lane);
+    build_rowmap(w, g, p, sg, M, lane);
     w.sync();
-    if (top) {                                                // any cell code | 7 == 7: one atomic OR per map, no RMW race
-        const int nm = g.LPn() + c0, nt = g.LPn() + r0;
-        if (needM) atomicOr(reinterpret_cast<unsigned*>(M + (r0 + g.V()) * g.pitchM() + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
-        if (needT) atomicOr(reinterpret_cast<unsigned*>(MT + (c0 + g.V()) * g.pitchT() + ((nt >> 3) << 2)), 7u << (4 * (nt & 7)));
+    if (top) {                                                // any cell code | 7 == 7: one atomic OR, no RMW race
+        const int nm = g.LPn() + c0;
+        atomicOr(reinterpret_cast<unsigned*>(M + (r0 + g.V()) * g.pitchM() + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
     }
     w.sync();
+    if (needT) {                                              // LEFT / RIGHT views read the transpose (agents included)
+        build_colmap(w, g, p, M, MT, lane);
+        w.sync();
+    }
 
     uint8_t* gobs = p.obs + (size_t)env * (p.n * g.AS());
     if (g.RP() == 32) gather_rows<4>(w, g, p, pmap, gobs, lane, abase_sh, astep);
@@ -734,109 +738,121 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
     __syncthreads();
     const int warp = threadIdx.x >> 5;
     const SW w(threadIdx.x & 31);
-    const int lane = w.lane;                                  // lane within the sub-warp that owns this env
-    const int env = p.env0 + (blockIdx.x * kWarps + warp) * SW::kEnvs + w.sub;
-    if (env >= p.env1) return;
-    if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
-
+    const int lane = w.lane;                                  // lane within the sub-warp that owns an env
     uint8_t* sg = smem + ((size_t)warp * SW::kEnvs + w.sub) * (g.GS() + g.PMS());
     uint8_t* pmap = sg + g.GS();
     const bool is_agent = lane < p.n;
-    const uint32_t gid = p.gid_base + (uint32_t)env;
-    // every global load of the step is issued up front; the map pre-fill below overlaps their latency
-    const uint32_t tick = p.tick[env];
-    const int t_prev = MODE == MODE_STEP ? p.t[env] : 0;
-    const int act = (MODE == MODE_STEP && is_agent) ? (int)p.actions[(size_t)env * p.n + lane] : 255;
-    int pos = -1 - lane, ori = 0, ep_ret = 0;
-    uint32_t a_rec = 0;
-    if (MODE != MODE_RESET && is_agent) {
-        a_rec = p.agent[(size_t)env * p.NA + lane];
-        ep_ret = p.ep_ret[(size_t)env * p.NA + lane];
-    }
-    const int n16 = g.GS() >> 4;
-    uint4 g0 = make_uint4(0, 0, 0, 0);
+    // One env instance per warp and per launch.  (A persistent loop over env instances was measured and dropped: warps that
+    // start together stay phase-locked -- everybody resolves moves, then everybody stores observations -- which turns a
+    // 65536-env launch into 14 back-to-back single-wave steps: Harvest 204 us instead of 167 us.  Letting the block scheduler
+    // start a fresh CTA whenever one retires decorrelates the phases; profiles/r2_notes.md.)
+    const int env = p.env0 + (blockIdx.x * kWarps + warp) * SW::kEnvs + w.sub;
+    if (env >= p.env1) return;
     {
-        const uint4* src = MODE == MODE_RESET ? reinterpret_cast<const uint4*>(p.map->base_grid)
-                                              : reinterpret_cast<const uint4*>(p.grid + (size_t)env * g.GS());
-        if (lane < n16) g0 = src[lane];
-        if (p.obs) fill_outside(w, g, p, pmap, lane);
-        if (lane < n16) reinterpret_cast<uint4*>(sg)[lane] = g0;
-        for (int i = lane + SW::kLanes; i < n16; i += SW::kLanes) reinterpret_cast<uint4*>(sg)[i] = src[i];
-    }
-    if (MODE != MODE_RESET && is_agent) {
-        pos = (int)(a_rec & 0xff) * g.W() + (int)((a_rec >> 8) & 0xff);
-        ori = (int)((a_rec >> 16) & 3);
-    }
-    w.sync();
+        if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
+        const uint32_t gid = p.gid_base + (uint32_t)env;
+        // every global load of the step is issued up front
+        const uint32_t tick = p.tick[env];
+        const int t_prev = MODE == MODE_STEP ? p.t[env] : 0;
+        const uint32_t cnt = MODE == MODE_STEP ? p.counts[env] : 0u;
+        const int act = (MODE == MODE_STEP && is_agent) ? (int)p.actions[(size_t)env * p.n + lane] : 255;
+        int pos = -1 - lane, ori = 0, ep_ret = 0;
+        uint32_t a_rec = 0;
+        if (MODE != MODE_RESET && is_agent) {
+            a_rec = p.agent[(size_t)env * p.NA + lane];
+            ep_ret = p.ep_ret[(size_t)env * p.NA + lane];
+        }
+        const int n16 = g.GS() >> 4;
+        {
+            const uint4* src = MODE == MODE_RESET ? reinterpret_cast<const uint4*>(p.map->base_grid)
+                                                  : reinterpret_cast<const uint4*>(p.grid + (size_t)env * g.GS());
+            uint4 g0 = make_uint4(0, 0, 0, 0);
+            if (lane < n16) g0 = src[lane];
+            if (p.obs) fill_outside(w, g, p, pmap, lane);     // "outside the map", while the state loads are in flight
+            if (lane < n16) reinterpret_cast<uint4*>(sg)[lane] = g0;
+            for (int i = lane + SW::kLanes; i < n16; i += SW::kLanes) reinterpret_cast<uint4*>(sg)[i] = src[i];
+        }
+        if (MODE != MODE_RESET && is_agent) {
+            pos = (int)(a_rec & 0xff) * g.W() + (int)((a_rec >> 8) & 0xff);
+            ori = (int)((a_rec >> 16) & 3);
+        }
+        w.sync();
 
-    if (MODE == MODE_STEP) {
-        int reward = 0, clean_num = 0;
-        update_moves(w, g, p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
-        // consume in index order: the lowest index on a cell eats the apple (253-256); mark occupancy
-        const unsigned same = w.match(pos);
-        const int here = is_agent ? sg[pos] : 0;
-        w.sync();
-        if (is_agent && lane == __ffs(same) - 1) {
-            if (here == SSD_CELL_APPLE) { reward += 1; sg[pos] = kOcc | SSD_CELL_EMPTY; }
-            else sg[pos] = (uint8_t)(kOcc | here);
+        int apples = (int)(cnt & 0xffffu), waste = (int)(cnt >> 16);
+        if (MODE == MODE_STEP) {
+            int reward = 0, clean_num = 0;
+            update_moves(w, g, p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
+            // consume in index order: the lowest index on a cell eats the apple (253-256); mark occupancy
+            const unsigned same = w.match(pos);
+            const int here = is_agent ? sg[pos] : 0;
+            const bool first = is_agent && lane == __ffs(same) - 1;
+            const unsigned ate = w.ballot(first && here == SSD_CELL_APPLE);
+            w.sync();
+            if (first) {
+                if (here == SSD_CELL_APPLE) { reward += 1; sg[pos] = kOcc | SSD_CELL_EMPTY; }
+                else sg[pos] = (uint8_t)(kOcc | here);
+            }
+            apples -= __popc(ate);
+            w.sync();
+            beams(w, g, p, sg, lane, is_agent, act, pos, ori, reward, clean_num, waste);              // 259-260
+            spawn(w, g, p, sg, lane, env, gid, tick, apples, waste);                                  // 263, 291-292
+            const int t = t_prev + 1;
+            if (is_agent) {
+                p.reward[(size_t)env * p.n + lane] = (int8_t)reward;
+                p.clean[(size_t)env * p.n + lane] = (uint8_t)clean_num;
+                ep_ret += reward;                                                               // 885-888
+            }
+            if (lane == 0) {
+                p.apple_cnt[env] = (uint16_t)apples;
+                p.done[env] = t >= p.episode_limit;                                             // 890-894
+                p.t[env] = t;
+                p.tick[env] = tick + 1;
+                p.counts[env] = (uint32_t)apples | ((uint32_t)waste << 16);
+            }
+        } else if (MODE == MODE_RESET) {
+            // setup_agents: agent i takes the free spawn point with the largest (key, cell) (map_env.py:771-784)
+            const bool is_sp = lane < p.n_spawn;
+            const int mycell = is_sp ? (int)__ldg(&p.map->spawn_pts[lane]) : -1;
+            bool taken = false;
+            for (int i = 0; i < p.n; ++i) {
+                uint32_t key = 0;
+                if (p.random_spawn && is_sp)
+                    key = p.d_spawnkey ? p.d_spawnkey[((size_t)env * p.n + i) * g.G() + mycell]
+                                       : philox_word(p, gid, tick, 3u, (uint32_t)(i * p.n_spawn + lane));
+                const bool cand = is_sp && !taken;
+                const uint32_t mk = w.rmax(cand ? key : 0u);
+                const unsigned eq = w.ballot(cand && key == mk);
+                const int win = 31 - __clz(eq);
+                const int cell = w.shfl(mycell, win);
+                if (lane == win) taken = true;
+                if (lane == i) pos = cell;
+            }
+            if (is_agent) {                                                                     // spawn_rotation (786-793)
+                if (p.spawn_rot >= 0) ori = p.spawn_rot;
+                else ori = p.d_rot ? (int)(p.d_rot[(size_t)env * p.n + lane] & 3) : (int)(philox_word(p, gid, tick, 4u, (uint32_t)lane) >> 30);
+            }
+            if (is_agent) sg[pos] |= kOcc;                         // distinct spawn points: no two lanes share a cell
+            w.sync();
+            apples = p.base_apples; waste = p.base_waste;
+            spawn(w, g, p, sg, lane, env, gid, tick, apples, waste);                                  // custom_map_update (313)
+            ep_ret = 0;
+            if (lane == 0) { p.t[env] = 0; p.tick[env] = tick + 1; p.counts[env] = (uint32_t)apples | ((uint32_t)waste << 16); }
         }
-        w.sync();
-        beams(w, g, p, sg, lane, is_agent, act, pos, ori, reward, clean_num);                     // 259-260
-        const int apples = spawn(w, g, p, sg, lane, env, gid, tick);                              // 263, 291-292
-        const int t = t_prev + 1;
-        if (is_agent) {
-            p.reward[(size_t)env * p.n + lane] = (int8_t)reward;
-            p.clean[(size_t)env * p.n + lane] = (uint8_t)clean_num;
-            ep_ret += reward;                                                               // 885-888
-        }
-        if (lane == 0) {
-            p.apple_cnt[env] = (uint16_t)apples;
-            p.done[env] = t >= p.episode_limit;                                             // 890-894
-            p.t[env] = t;
-            p.tick[env] = tick + 1;
-        }
-    } else if (MODE == MODE_RESET) {
-        // setup_agents: agent i takes the free spawn point with the largest (key, cell) (map_env.py:771-784)
-        const bool is_sp = lane < p.n_spawn;
-        const int mycell = is_sp ? (int)__ldg(&p.map->spawn_pts[lane]) : -1;
-        bool taken = false;
-        for (int i = 0; i < p.n; ++i) {
-            uint32_t key = 0;
-            if (p.random_spawn && is_sp)
-                key = p.d_spawnkey ? p.d_spawnkey[((size_t)env * p.n + i) * g.G() + mycell]
-                                   : philox_word(p, gid, tick, 3u, (uint32_t)(i * p.n_spawn + lane));
-            const bool cand = is_sp && !taken;
-            const uint32_t mk = w.rmax(cand ? key : 0u);
-            const unsigned eq = w.ballot(cand && key == mk);
-            const int win = 31 - __clz(eq);
-            const int cell = w.shfl(mycell, win);
-            if (lane == win) taken = true;
-            if (lane == i) pos = cell;
-        }
-        if (is_agent) {                                                                     // spawn_rotation (786-793)
-            if (p.spawn_rot >= 0) ori = p.spawn_rot;
-            else ori = p.d_rot ? (int)(p.d_rot[(size_t)env * p.n + lane] & 3) : (int)(philox_word(p, gid, tick, 4u, (uint32_t)lane) >> 30);
-        }
-        if (is_agent) sg[pos] |= kOcc;                         // distinct spawn points: no two lanes share a cell
-        w.sync();
-        spawn(w, g, p, sg, lane, env, gid, tick);                                                 // custom_map_update (313)
-        ep_ret = 0;
-        if (lane == 0) { p.t[env] = 0; p.tick[env] = tick + 1; }
-    }
 
-    if (MODE != MODE_RENDER) {                                 // strip the occupancy bits, write the state back
-        const unsigned same = w.match(pos);
-        if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
-        w.sync();
-        uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * g.GS());
-        warp_for<SW::kLanes>(g.GS() >> 4, lane, [&](int i) { dst[i] = reinterpret_cast<const uint4*>(sg)[i]; });
-        if (is_agent) {
-            const int r = g.divW(pos);
-            p.agent[(size_t)env * p.NA + lane] = (uint32_t)r | ((uint32_t)(pos - r * g.W()) << 8) | ((uint32_t)ori << 16);
-            p.ep_ret[(size_t)env * p.NA + lane] = ep_ret;
+        if (MODE != MODE_RENDER) {                                 // strip the occupancy bits, write the state back
+            const unsigned same = w.match(pos);
+            if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
+            w.sync();
+            uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * g.GS());
+            warp_for<SW::kLanes>(g.GS() >> 4, lane, [&](int i) { dst[i] = reinterpret_cast<const uint4*>(sg)[i]; });
+            if (is_agent) {
+                const int r = g.divW(pos);
+                p.agent[(size_t)env * p.NA + lane] = (uint32_t)r | ((uint32_t)(pos - r * g.W()) << 8) | ((uint32_t)ori << 16);
+                p.ep_ret[(size_t)env * p.NA + lane] = ep_ret;
+            }
         }
+        if (p.obs || p.state_rgb) render(w, g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
     }
-    if (p.obs || p.state_rgb) render(w, g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
 }
 
 // ------------------------------------------------------------------ incentive bookkeeping (homophily_learner.py:98-115)
@@ -903,10 +919,10 @@ struct ssd_handle {
 };
 
 static int fill_common(const ssd_handle* h, const ssd_state* st, const ssd_draws* d, KParams& k) {
-    if (!h || !st || !st->grid || !st->agent || !st->ep_ret || !st->t || !st->tick) return SSD_ERR_INVALID;
+    if (!h || !st || !st->grid || !st->agent || !st->ep_ret || !st->t || !st->tick || !st->counts) return SSD_ERR_INVALID;
     k = h->kp;
     k.env0 = 0; k.env1 = k.B;
-    k.grid = st->grid; k.agent = st->agent; k.ep_ret = st->ep_ret; k.t = st->t; k.tick = st->tick;
+    k.grid = st->grid; k.agent = st->agent; k.ep_ret = st->ep_ret; k.t = st->t; k.tick = st->tick; k.counts = st->counts;
     if (d) {
         if ((d->u_waste == nullptr) != (d->wkey == nullptr)) return SSD_ERR_INVALID;
         k.d_prio = d->prio; k.d_uapple = d->u_apple; k.d_uwaste = d->u_waste; k.d_wkey = d->wkey;
@@ -932,8 +948,9 @@ static int launch_lpe(ssd_handle* h, const KParams& k, void* stream) {
         }
     }
     const int envs_per_cta = kWarps * (32 / LPE);
-    const int grid = (k.env1 - k.env0 + envs_per_cta - 1) / envs_per_cta;
+    int grid = (k.env1 - k.env0 + envs_per_cta - 1) / envs_per_cta;
     if (grid <= 0) return SSD_OK;
+
     ssd_kernel<MODE, GEO, LPE><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
     ++h->launches;
     SSD_CUDA(cudaGetLastError());
@@ -1041,6 +1058,8 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     k.episode_limit = cfg->episode_limit; k.fire_cost = cfg->fire_cost; k.hit_penalty = cfg->hit_penalty;
     k.beam_len = cfg->beam_len; k.n_actions = cfg->kind == SSD_KIND_CLEANUP ? 9 : 8;
     k.n_apple = na; k.n_waste = nw; k.n_spawn = ns; k.n_apple4 = (na + 3) / 4; k.n_waste2 = (nw + 1) / 2;
+    k.base_apples = 0; k.base_waste = 0;
+    for (int c = 0; c < G; ++c) { k.base_apples += hm->base_grid[c] == SSD_CELL_APPLE; k.base_waste += hm->base_grid[c] == SSD_CELL_WASTE; }
     k.random_spawn = cfg->random_spawn_point != 0; k.spawn_rot = cfg->spawn_rotation < 0 ? -1 : cfg->spawn_rotation;
     k.invN20 = magic20(k.N, SSD_MAX_AGENTS * k.N + 64); k.invW20 = magic20(W, G + 1);
     k.seed_lo = (uint32_t)cfg->seed; k.seed_hi = (uint32_t)(cfg->seed >> 32); k.gid_base = cfg->env_gid_base;

@@ -94,6 +94,15 @@ class MacFrontEnd:
             return self.original(x)
         return self._front_end().forward_env(self.env)
 
+    def __deepcopy__(self, memo):
+        """``copy.deepcopy(mac)`` (the learner's target network, homophily_learner.py:47) must not copy the kernel handle: the
+        copy of the agent gets its own, unpatched ``rgb_preprocess`` back."""
+        import types
+        agent_copy = memo.get(id(self.mac.agent))
+        if agent_copy is None:
+            return self.original
+        return types.MethodType(type(self.mac.agent).rgb_preprocess, agent_copy)
+
     def detach(self):
         self.mac.agent.rgb_preprocess = self.original
         if self._fe is not None:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SSD_B200_ABI_VERSION 1
+#define SSD_B200_ABI_VERSION 2
 
 #define SSD_OK             0
 #define SSD_ERR_INVALID   -1   /* bad argument / unsupported geometry            */
@@ -97,6 +97,9 @@ typedef struct ssd_state {
     int32_t*  ep_ret;    /* [B][agent_stride]  episode return per agent (map_env.py:885-888) */
     int32_t*  t;         /* [B]                _episode_steps                             */
     uint32_t* tick;      /* [B]                Philox step counter (never reset)          */
+    uint32_t* counts;    /* [B]                #'A' cells | #'H' cells << 16 of `grid` (the reference recounts the map every
+                          *                     step: map_env.py:291-292, cleanup.py:206-212).  Whoever writes `grid` directly
+                          *                     must refresh this word; ssd_reset / ssd_step keep it up to date              */
 } ssd_state;
 
 /* Outputs of one step == (reward, terminated, info) of MapEnv.step + get_obs/get_state. */

@@ -12,6 +12,10 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "needs_reference: needs the unmodified reference under /root/reference")
+    # the unmodified reference indexes tensors with lists (episode_buffer.py) and builds tensors from lists of ndarrays
+    config.addinivalue_line("filterwarnings", "ignore:Using a non-tuple sequence:UserWarning")
+    config.addinivalue_line("filterwarnings", "ignore:Creating a tensor from a list of numpy:UserWarning")
+    config.addinivalue_line("filterwarnings", "ignore:invalid escape sequence:SyntaxWarning")
 
 
 def pytest_collection_modifyitems(config, items):

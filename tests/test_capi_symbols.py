@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_capi.EXPORTS) == names
-    assert lib.ssd_abi_version() == 1
+    assert lib.ssd_abi_version() == 2
     assert lib.ssd_error_string(-3).decode().startswith("There are not enough spawn points")
 
 
