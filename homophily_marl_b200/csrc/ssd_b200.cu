@@ -64,6 +64,7 @@ struct KParams {
     int env0, env1;                           // this launch covers env instances [env0, env1) of the B resident ones
     int GS, NA, RP, PS, AS, ES;               // strides (ssd_layout)
     int pitchM, pitchT, off_map[4], PMS;      // nibble maps M / MT: row pitches, byte offset by orientation (0,1 -> MT; 2,3 -> M), total bytes
+    int direct, padF, padB;                   // direct-gather render (small views): slack bytes before / after the staged grid
     int LPn, nw8M, nw8T;                      // left pad in nibbles (V rounded up to 8), words per map row holding cells
     uint32_t maskM8, maskT8;                  // valid-nibble mask of the last word of a map row
     int agents_uniform;                       // all agent colours equal -> no per-agent repaint
@@ -92,6 +93,8 @@ struct KParams {
 // arithmetic folds into immediates; any other geometry runs the same code on runtime values (GeoD).
 struct GeoVals {
     int kind, H, W, V, G, GS, N, RP, PS, AS, LPn, nw8M, nw8T, pitchM, pitchT, off0, off1, off2, off3, PMS;
+    int direct, padF, padB;                   // small views (RP <= 16) are gathered straight from the staged grid: no maps, but
+                                              // V rows of slack before / after the grid so that column runs need no bounds test
     uint32_t maskM8, maskT8;
 };
 __host__ __device__ constexpr int cround_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -109,6 +112,10 @@ __host__ __device__ constexpr GeoVals make_geo(int kind, int H, int W, int V) {
     const int szM = cround_up((H + 2 * V) * g.pitchM, 16) + 16, szT = cround_up((W + 2 * V) * g.pitchT, 16) + 16;
     g.off0 = 16; g.off1 = 16; g.off2 = 16 + szT; g.off3 = 16 + szT;        // by orientation: LEFT/RIGHT -> MT, UP/DOWN -> M
     g.PMS = szT + szM + 32;
+    g.direct = g.RP <= 16;
+    g.padF = g.direct ? cround_up(V * W + 16, 16) : 16;
+    g.padB = g.direct ? cround_up(V * W + 32, 16) : 32;
+    if (g.direct) g.PMS = 0;
     return g;
 }
 
@@ -132,6 +139,9 @@ struct GeoS {                                                 // compile-time ge
     __device__ __forceinline__ int pitchM() const { return v.pitchM; }
     __device__ __forceinline__ int pitchT() const { return v.pitchT; }
     __device__ __forceinline__ int PMS() const { return v.PMS; }
+    __device__ __forceinline__ bool direct() const { return v.direct != 0; }
+    __device__ __forceinline__ int padF() const { return v.padF; }
+    __device__ __forceinline__ int padB() const { return v.padB; }
     __device__ __forceinline__ uint32_t maskM8() const { return v.maskM8; }
     __device__ __forceinline__ int off_map(int o) const { return o == 0 ? v.off0 : (o == 1 ? v.off1 : (o == 2 ? v.off2 : v.off3)); }
     __device__ __forceinline__ int divW(int x) const { return (int)((unsigned)x / (unsigned)v.W); }
@@ -158,6 +168,9 @@ struct GeoD {                                                 // runtime geometr
     __device__ __forceinline__ int pitchM() const { return p.pitchM; }
     __device__ __forceinline__ int pitchT() const { return p.pitchT; }
     __device__ __forceinline__ int PMS() const { return p.PMS; }
+    __device__ __forceinline__ bool direct() const { return p.direct != 0; }
+    __device__ __forceinline__ int padF() const { return p.padF; }
+    __device__ __forceinline__ int padB() const { return p.padB; }
     __device__ __forceinline__ uint32_t maskM8() const { return p.maskM8; }
     __device__ __forceinline__ int off_map(int o) const { return p.off_map[o]; }
     __device__ __forceinline__ int divW(int x) const { return (int)(((uint32_t)x * p.invW20) >> 20); }
@@ -646,6 +659,86 @@ __device__ __forceinline__ void fill_outside(const SW& w, const GEO& g, const KP
     for (int i = lane; i < n16; i += SW::kLanes) q[i] = v6;           // trip count is a compile-time constant for the shipped maps
 }
 
+// Direct gather for small views (N <= 16, i.e. every Cleanup configuration): a lane owns one (agent, y) output row and
+// reads its N cells straight from the staged byte grid -- one unaligned 16-byte run for UP / DOWN (5 aligned words + funnel
+// shifts), N byte loads down a column for LEFT / RIGHT -- packs them to nibbles, replaces the cells outside the map by
+// index 6, reverses the run for DOWN / RIGHT, and colours 4 pixels per PRMT as the map path does.  No padded maps are built.
+// The grid tile has V rows of slack on both sides (zeroed at kernel start), so no load needs a bounds test; agents were
+// written into the staged grid as index 7 by the caller.
+template <class SW, class GEO>
+__device__ __forceinline__ void gather_direct(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* gobs, int lane,
+                                              bool is_agent, int r0, int c0, int ori) {
+    const int N = g.N(), V = g.V(), W = g.W(), units = p.n * N, WR = g.RP() >> 2;
+    const uint32_t apack = (uint32_t)r0 | ((uint32_t)c0 << 8) | ((uint32_t)ori << 16);
+    const uint32_t lastmask = 0xffffffffu >> (8 * (4 * WR - N));
+    for (int u0 = 0; u0 < units; u0 += SW::kLanes) {
+        const int u = u0 + lane;
+        const bool valid = u < units;
+        const int al = valid ? g.divN(u) : 0;
+        const int y = u - al * N;
+        const uint32_t ap = w.shfl(apack, al);
+        if (!valid) continue;
+        const int ar = (int)(ap & 0xffu), ac = (int)((ap >> 8) & 0xffu), o = (int)(ap >> 16);
+        uint32_t b0, b1, b2, b3;                              // element i of the run (ascending map coordinate) in byte i
+        int lo, hi;                                           // elements inside the map: [lo, hi)
+        if (o >= 2) {                                         // UP / DOWN: a run along map row R
+            const int R = o == 2 ? ar - V + y : ar + V - y;
+            const bool rv = (unsigned)R < (unsigned)g.H();
+            lo = rv ? max(0, V - ac) : 0;
+            hi = rv ? min(N, W + V - ac) : 0;
+            const int start = (rv ? R : 0) * W + ac - V;      // >= -V: inside the front slack
+            SSD_CHECK(start >= -g.padF() && start + 20 <= g.GS() + g.padB());
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(sg + (start & ~3));
+            const uint32_t sh = (uint32_t)(start & 3) * 8u;
+            const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
+            b0 = __funnelshift_r(a0, a1, sh); b1 = __funnelshift_r(a1, a2, sh);
+            b2 = __funnelshift_r(a2, a3, sh); b3 = __funnelshift_r(a3, a4, sh);
+        } else {                                              // LEFT / RIGHT: a run down map column C
+            const int C = o == 0 ? ac + V - y : ac - V + y;
+            const bool cv = (unsigned)C < (unsigned)W;
+            lo = cv ? max(0, V - ar) : 0;
+            hi = cv ? min(N, g.H() + V - ar) : 0;
+            const uint8_t* col = sg + (ar - V) * W + (cv ? C : 0);     // rows ar-V .. ar+V: at most V rows into either slack
+            SSD_CHECK((ar - V) * W >= -g.padF() && (ar + V) * W + W <= g.GS() + g.padB());
+            uint32_t e[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) e[i] = i < N ? (uint32_t)col[i * W] : 0u;
+            b0 = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
+            b1 = e[4] | (e[5] << 8) | (e[6] << 16) | (e[7] << 24);
+            b2 = e[8] | (e[9] << 8) | (e[10] << 16) | (e[11] << 24);
+            b3 = e[12] | (e[13] << 8) | (e[14] << 16) | (e[15] << 24);
+        }
+        // bytes -> nibbles (every byte is a colour index < 8), cells outside the map -> 6
+        uint32_t n0 = prmt(b0 | (b0 >> 4), b1 | (b1 >> 4), 0x6420);
+        uint32_t n1 = prmt(b2 | (b2 >> 4), b3 | (b3 >> 4), 0x6420);
+        const unsigned long long vm = (hi >= 16 ? ~0ull : ((1ull << (4 * hi)) - 1ull)) & ~((1ull << (4 * lo)) - 1ull);
+        const uint32_t m0 = (uint32_t)vm, m1 = (uint32_t)(vm >> 32);
+        n0 = (n0 & m0) | (0x66666666u & ~m0);
+        n1 = (n1 & m1) | (0x66666666u & ~m1);
+        if (o & 1) {                                          // RIGHT / DOWN: out[x] = element N-1-x (np.rot90 k=3 / k=2)
+            const uint32_t r1 = nibble_reverse(n0), r0w = nibble_reverse(n1);       // nibble j of (r1:r0w) = element 15-j
+            const unsigned long long rr = (((unsigned long long)r1 << 32) | r0w) >> (4 * (16 - N));   // up to 60 bits for tiny views
+            n0 = (uint32_t)rr;
+            n1 = (uint32_t)(rr >> 32);
+        }
+        const uint32_t v[4] = { n0, n0 >> 16, n1, n1 >> 16 };
+        uint8_t* dst = gobs + al * g.AS() + y * g.RP();
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            const uint32_t t0 = p.lut8[2 * pl], t1 = p.lut8[2 * pl + 1];
+            uint32_t o4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o4[k] = prmt(t0, t1, v[k]);
+            if (WR == 4) { o4[3] &= lastmask; st_row16(dst + pl * g.PS(), o4); }
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < WR) *reinterpret_cast<uint32_t*>(dst + pl * g.PS() + 4 * k) = k == WR - 1 ? (o4[k] & lastmask) : o4[k];
+            }
+        }
+    }
+}
+
 template <class SW, class GEO>
 __device__ __forceinline__ void render(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
                                        int lane, bool is_agent, int pos, int ori, int env) {
@@ -667,38 +760,35 @@ __device__ __forceinline__ void render(const SW& w, const GEO& g, const KParams&
         }
     }
     if (!p.obs) return;
-
-    // the maps were pre-filled with "outside the map" at kernel start (fill_outside); now the cells, then the agents
-    // per agent: which map, first word of its window row 0, row step, funnel shift, direction   (o: 0 LEFT 1 RIGHT 2 UP 3 DOWN)
-    const bool colmap = ori < 2, rev = (ori == 1) || (ori == 3);
-    const int rowc = colmap ? c0 : r0;                        // coordinate that selects the map row
-    const int runc = colmap ? r0 : c0;                        // coordinate along the run
-    const int pitch = colmap ? g.pitchT() : g.pitchM();
-    const bool down = (ori == 0) || (ori == 3);               // window row y walks towards smaller map rows
-    const int s = g.LPn() + runc + (rev ? g.V() : -g.V());    // first pixel of the run (highest nibble when descending)
-    const uint32_t abase_sh = (uint32_t)(g.off_map(ori) + (rowc + (down ? 2 * g.V() : 0)) * pitch + ((s >> 3) << 2))
-                              | ((uint32_t)((rev ? 7 - (s & 7) : (s & 7)) * 4) << 16) | ((uint32_t)rev << 24);
-    const int astep = down ? -pitch : pitch;
-    const bool needT = w.ballot(is_agent && ori < 2) != 0;
-    w.sync();
-    uint8_t* MT = pmap + g.off_map(0);
-    uint8_t* M = pmap + g.off_map(2);
-    build_rowmap(w, g, p, sg, M, lane);
-    w.sync();
-    if (top) {                                                // any cell code | 7 == 7: one atomic OR, no RMW race
-        const int nm = g.LPn() + c0;
-        atomicOr(reinterpret_cast<unsigned*>(M + (r0 + g.V()) * g.pitchM() + ((nm >> 3) << 2)), 7u << (4 * (nm & 7)));
-    }
-    w.sync();
-    if (needT) {                                              // LEFT / RIGHT views read the transpose (agents included)
-        build_colmap(w, g, p, M, MT, lane);
-        w.sync();
-    }
-
     uint8_t* gobs = p.obs + (size_t)env * (p.n * g.AS());
-    if (g.RP() == 32) gather_rows<4>(w, g, p, pmap, gobs, lane, abase_sh, astep);
-    else if (g.RP() == 16) gather_rows<2>(w, g, p, pmap, gobs, lane, abase_sh, astep);
-    else gather_rows<0>(w, g, p, pmap, gobs, lane, abase_sh, astep);
+
+    if (g.direct()) {
+        gather_direct(w, g, p, sg, gobs, lane, is_agent, r0, c0, ori);
+    } else {
+        // the maps were pre-filled with "outside the map" at kernel start (fill_outside); now the cells (agents are already in
+        // the staged grid as index 7)
+        // per agent: which map, first word of its window row 0, row step, funnel shift, direction   (o: 0 LEFT 1 RIGHT 2 UP 3 DOWN)
+        const bool colmap = ori < 2, rev = (ori == 1) || (ori == 3);
+        const int rowc = colmap ? c0 : r0;                        // coordinate that selects the map row
+        const int runc = colmap ? r0 : c0;                        // coordinate along the run
+        const int pitch = colmap ? g.pitchT() : g.pitchM();
+        const bool down = (ori == 0) || (ori == 3);               // window row y walks towards smaller map rows
+        const int s = g.LPn() + runc + (rev ? g.V() : -g.V());    // first pixel of the run (highest nibble when descending)
+        const uint32_t abase_sh = (uint32_t)(g.off_map(ori) + (rowc + (down ? 2 * g.V() : 0)) * pitch + ((s >> 3) << 2))
+                                  | ((uint32_t)((rev ? 7 - (s & 7) : (s & 7)) * 4) << 16) | ((uint32_t)rev << 24);
+        const int astep = down ? -pitch : pitch;
+        const bool needT = w.ballot(is_agent && ori < 2) != 0;
+        uint8_t* MT = pmap + g.off_map(0);
+        uint8_t* M = pmap + g.off_map(2);
+        build_rowmap(w, g, p, sg, M, lane);
+        w.sync();
+        if (needT) {                                              // LEFT / RIGHT views read the transpose (agents included)
+            build_colmap(w, g, p, M, MT, lane);
+            w.sync();
+        }
+        if (g.RP() == 32) gather_rows<4>(w, g, p, pmap, gobs, lane, abase_sh, astep);
+        else gather_rows<0>(w, g, p, pmap, gobs, lane, abase_sh, astep);
+    }
     const int tail = g.AS() - 3 * g.PS();                         // pad bytes per agent block (0 for the shipped views)
     if (tail) for (int i = lane; i < p.n * (tail >> 2); i += SW::kLanes)
         *reinterpret_cast<uint32_t*>(gobs + (i / (tail >> 2)) * g.AS() + 3 * g.PS() + 4 * (i % (tail >> 2))) = 0u;
@@ -739,8 +829,10 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
     const int warp = threadIdx.x >> 5;
     const SW w(threadIdx.x & 31);
     const int lane = w.lane;                                  // lane within the sub-warp that owns an env
-    uint8_t* sg = smem + ((size_t)warp * SW::kEnvs + w.sub) * (g.GS() + g.PMS());
-    uint8_t* pmap = sg + g.GS();
+    // per-env tile: [front slack][grid GS][back slack][nibble maps (map path only)]
+    uint8_t* tile = smem + ((size_t)warp * SW::kEnvs + w.sub) * (g.padF() + g.GS() + g.padB() + g.PMS());
+    uint8_t* sg = tile + g.padF();
+    uint8_t* pmap = sg + g.GS() + g.padB();
     const bool is_agent = lane < p.n;
     // One env instance per warp and per launch.  (A persistent loop over env instances was measured and dropped: warps that
     // start together stay phase-locked -- everybody resolves moves, then everybody stores observations -- which turns a
@@ -768,7 +860,12 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
                                                   : reinterpret_cast<const uint4*>(p.grid + (size_t)env * g.GS());
             uint4 g0 = make_uint4(0, 0, 0, 0);
             if (lane < n16) g0 = src[lane];
-            if (p.obs) fill_outside(w, g, p, pmap, lane);     // "outside the map", while the state loads are in flight
+            if (p.obs) {                                      // while the state loads are in flight
+                if (g.direct()) {                             // zero the slack around the grid (read, then masked, by the gather)
+                    for (int i = lane; i < (g.padF() >> 4); i += SW::kLanes) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
+                    for (int i = lane; i < (g.padB() >> 4); i += SW::kLanes) reinterpret_cast<uint4*>(sg + g.GS())[i] = make_uint4(0, 0, 0, 0);
+                } else fill_outside(w, g, p, pmap, lane);     // "outside the map"
+            }
             if (lane < n16) reinterpret_cast<uint4*>(sg)[lane] = g0;
             for (int i = lane + SW::kLanes; i < n16; i += SW::kLanes) reinterpret_cast<uint4*>(sg)[i] = src[i];
         }
@@ -851,7 +948,14 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
                 p.ep_ret[(size_t)env * p.NA + lane] = ep_ret;
             }
         }
-        if (p.obs || p.state_rgb) render(w, g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
+        if (p.obs || p.state_rgb) {
+            // agent overlay: every occupied cell shows an agent (index 7; which agent only matters for the full-colour repaint and
+            // the state image, both handled in render).  Same value from every lane on a shared cell: no race.
+            w.sync();                                          // the write-back above has read the staged grid
+            if (is_agent) sg[pos] = 7;
+            w.sync();
+            render(w, g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
+        }
     }
 }
 
@@ -1054,6 +1158,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
     k.RP = gv.RP; k.PS = gv.PS; k.AS = gv.AS; k.ES = n * k.AS;
     k.LPn = gv.LPn; k.nw8M = gv.nw8M; k.nw8T = gv.nw8T; k.maskM8 = gv.maskM8; k.maskT8 = gv.maskT8;
     k.pitchM = gv.pitchM; k.pitchT = gv.pitchT; k.PMS = gv.PMS;
+    k.direct = gv.direct; k.padF = gv.padF; k.padB = gv.padB;
     k.off_map[0] = gv.off0; k.off_map[1] = gv.off1; k.off_map[2] = gv.off2; k.off_map[3] = gv.off3;
     k.episode_limit = cfg->episode_limit; k.fire_cost = cfg->fire_cost; k.hit_penalty = cfg->hit_penalty;
     k.beam_len = cfg->beam_len; k.n_actions = cfg->kind == SSD_KIND_CLEANUP ? 9 : 8;
@@ -1077,7 +1182,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
 
     k.invMW20 = magic20(k.nw8M, H * k.nw8M + 32); k.invMTW20 = magic20(k.nw8T, W * k.nw8T + 32);
     if (k.invMW20 == 0 || k.invMTW20 == 0 || k.PMS >= 60000) { delete hm; delete h; return SSD_ERR_INVALID; }
-    k.off_pmap = k.GS;
+    k.off_pmap = k.padF + k.GS + k.padB;
     k.smem_per_warp = k.off_pmap + k.PMS;
     // two envs per warp need the spawn points (reset) and the per-lane apple decision bits (64) to fit 16 lanes
     h->lanes_per_env = 32;
