@@ -126,6 +126,9 @@ def register_b200() -> None:
     import components.action_selectors as ref_selectors
     from homophily_marl_b200 import selectors
     ref_selectors.REGISTRY.update(selectors.REGISTRY)        # 'epsilon_greedy_b200': one kernel instead of seven torch launches
+    import learners as ref_learners
+    from homophily_marl_b200 import learner
+    ref_learners.REGISTRY.update(learner.REGISTRY)           # 'homophily_learner_b200': incentive kernel, device clusters, DP all-reduce
 
 
 def _python_bool_terminated(ctor):

@@ -248,7 +248,8 @@ def run_reference(a):
 def train_e2e(a, which=("b200", "b200_batched", "reference")):
     """`run.run_sequential` of the UNCHANGED reference (rollouts + replay + HomophilyLearner updates + test episodes),
     Cleanup default3 / 3 agents / yaml hyper-parameters, t_max env steps: on the CUDA env through the reference's own
-    single-env EpisodeRunner ('b200'), through BatchedEpisodeRunner at B=256 ('b200_batched', 20 x t_max env steps), and on
+    single-env EpisodeRunner ('b200'), through BatchedEpisodeRunner at B=256 with the fused u8 front end, the device epsilon-greedy
+    selector and DeviceHomophilyLearner ('b200_batched', 20 x t_max env steps; MAC and replay buffer are the reference's), and on
     the reference's own CPU env ('reference').  env-steps/s = train env steps / wall seconds (test episodes are extra work)."""
     from baseline import refloop
     out = {"what": "run_sequential, Cleanup default3, 3 agents, homophily IQL, yaml defaults; env-steps/s incl. learner updates + tests",
@@ -275,7 +276,9 @@ def train_e2e(a, which=("b200", "b200_batched", "reference")):
                 B = 256
                 t_max = 20 * a.train_t_max
                 cfg = refloop.load_config("cleanup", t_max=t_max, runner="batched", batch_size_run=B, buffer_size=4 * B,
-                                          buffer_cpu_only=False, **{**common, "test_nepisode": B, "test_interval": t_max})
+                                          buffer_cpu_only=False, fused_frontend=True, action_selector="epsilon_greedy_b200",
+                                          learner="homophily_learner_b200",
+                                          **{**common, "test_nepisode": B, "test_interval": t_max})
                 per_run = B * LIMIT
             else:
                 t_max = a.train_t_max
