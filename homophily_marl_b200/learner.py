@@ -29,6 +29,19 @@ from .incentive import incentive_rewards
 _NEG = -9999999.0                                             # homophily_learner.py:131-132
 
 
+def _clone_mac(mac):
+    """``copy.deepcopy(mac)`` (homophily_learner.py:47) that also works on a MAC which has already been rolled out: hidden states
+    and cached inputs carrying autograd history cannot be deep-copied and are re-created by ``init_hidden`` anyway."""
+    parked = {k: v for k, v in vars(mac).items() if torch.is_tensor(v) and v.grad_fn is not None}
+    for k in parked:
+        object.__setattr__(mac, k, None)
+    try:
+        return copy.deepcopy(mac)
+    finally:
+        for k, v in parked.items():
+            object.__setattr__(mac, k, v)
+
+
 class FlatBucket:
     """One contiguous fp32 buffer over the gradients of a parameter list: a single all-reduce per optimiser step."""
 
@@ -93,7 +106,7 @@ class DeviceHomophilyLearner:
         self.last_target_update_episode = 0
         self.optimiser_env = Adam(params=self.params_env, lr=args.lr_env)
         self.optimiser_inc = Adam(params=self.params_inc, lr=args.lr_inc)
-        self.target_mac = copy.deepcopy(mac)
+        self.target_mac = _clone_mac(mac)
         self.log_stats_t = -self.args.learner_log_interval - 1
         self.group = process_group
         self.bucket = FlatBucket(list(self.params_inc) + list(self.params_env), group=process_group)

@@ -155,8 +155,13 @@ def test_batched_runner_with_fused_front_end_and_device_selector():
     # the fused features equal the module's on the stored fp32 observations (tolerance: tests/test_gpu_frontend.py)
     t = 7
     x = batch["obs"][:, t].reshape(B * 3, 3, 15, 15)
-    with torch.no_grad():
-        want = c.runner.front.original(x)
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False      # the reference module in true fp32
+    try:
+        with torch.no_grad():
+            want = c.runner.front.original(x)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
     c.runner.env.obs_buf.zero_()
     lay = c.runner.env.layout
     u8 = (batch["obs"][:, t] * 256).to(torch.uint8)
