@@ -57,8 +57,9 @@ def parse():
     ap.add_argument("--workload", default="harvest5_b4096", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--replays", type=int, default=0, help="timed replays of the K-step schedule (0 = auto, >= 5)")
-    ap.add_argument("--groups", type=int, default=1,
-                    help="step the batch as G independent env ranges on G streams (SSDBatchEnv.step_range, asynchronous sampler)")
+    ap.add_argument("--groups", type=int, default=0,
+                    help="step the batch as G independent env ranges on G streams (SSDBatchEnv.step_range, the asynchronous-sampler "
+                         "API BatchedEpisodeRunner uses with args.env_groups); 0 = auto: 4 for single-wave batches (<= 8192 envs), else 1")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--random-spawn", action="store_true")
@@ -483,6 +484,17 @@ def run_b200(a):
     cfg = workload_config(a, world)
     B, n = cfg["envs_per_gpu"], cfg["num_agents"]
     K, R = a.steps, auto_replays(a, a.steps)
+    if a.groups <= 0:                                         # one wave of warps cannot overlap its own logic and store phases
+        a.groups = 4 if (B <= 8192 and B % 4 == 0) else 1
+    single = None
+    if a.groups > 1:                                          # the same K steps as ONE launch per step, for the record
+        r1, ro1 = measure(cfg, a, dev, rank, world, K, a.warmup, max(5, R // 4), groups=1, dist=dist)
+        single = {"us_per_step": r1["ms_per_step"] * 1e3, "value": r1["value"],
+                  "frac": r1["alg_bytes"] / (r1["ms_per_step"] * 1e-3) / 1e9 / hbm_peak()[0],
+                  "what": "same workload, one ssd_step launch per step over the whole batch (--groups 1)"}
+        ro1.close()
+        del ro1
+        torch.cuda.empty_cache()
     res, ro = measure(cfg, a, dev, rank, world, K, a.warmup, R, groups=a.groups, clock=clk, dist=dist)
     env = ro.env
     peak, peak_src = hbm_peak()
@@ -563,8 +575,13 @@ def run_b200(a):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "ssd_kernel<MODE_STEP>", "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": res["alg_bytes"] // max(a.groups, 1),
+                             "launches_per_step": max(a.groups, 1),
+                             "achieved_how": "algorithmic bytes of one step over the whole batch / median step time (a step = "
+                                             f"{max(a.groups, 1)} concurrent range launch(es))",
                              "bytes_per_env_step": res["bytes_per_env_step"],
                              "avg_launch_us": res["ms_per_step"] * 1e3}}
+        if single is not None:
+            line["single_launch"] = single
         if affinity:
             line["cpu_affinity"] = f"{len(affinity)} cpus (nvmlDeviceSetCpuAffinity)"
         if extra:

@@ -13,7 +13,8 @@ constantly False in the reference, agent.py:192,243):
   * ``collective_return`` / ``equality_metric`` are summed over the B envs into the stats dict exactly as B
     successive single-env episodes would;
   * the step loop never synchronises with the host: ``terminated`` is the host-side step count (all envs share
-    ``episode_limit``), and the state image comes out of the same launch as the step (``ssd_step_out.state_rgb``).
+    ``episode_limit``), and the state image comes out of the same launch as the step (``ssd_step_out.state_rgb``);
+  * ``args.env_groups = G`` rolls the batch out as G env ranges on G streams (asynchronous sampler, ``ssd_step_range``).
 """
 from __future__ import annotations
 
@@ -54,6 +55,12 @@ class BatchedEpisodeRunner:
             avail[7] = 0
         self._avail = torch.tensor(avail, dtype=torch.int32, device=e.device).expand(e.B, e.n, e.n_actions).contiguous()
         self._orient_vec = torch.as_tensor(mapspec.ORIENT_VEC, dtype=torch.float32, device=e.device)
+        self.groups = max(1, int(getattr(self.args, "env_groups", 1) or 1))
+        if self.batch_size % self.groups:
+            raise ValueError("env_groups must divide batch_size_run")
+        self._streams = [torch.cuda.Stream(device=e.device) for _ in range(self.groups)] if self.groups > 1 else []
+        self._actions_u8 = torch.zeros((e.B, e.n), dtype=torch.uint8, device=e.device)
+        self.front = None
 
     # ---- reference surface ------------------------------------------------------------------------------
     def setup(self, scheme, groups, preprocess, mac, batch_cls=None):
@@ -93,11 +100,42 @@ class BatchedEpisodeRunner:
         self.t = 0
 
     # ---- device-side views of what the reference env returns per step -------------------------------------
-    def _pre_transition(self):
+    def _pre_transition(self, sl=slice(None)):
         e = self.env                                          # obs AND state image were written by the last step / reset launch
-        return {"state": e.state_rgb.float() / 256, "avail_actions": self._avail,
-                "obs": e.obs_view().float() / 256, "agent_pos": e.agent_pos.float(),
-                "agent_orientation": self._orient_vec[e.agent_orient.long()]}
+        return {"state": e.state_rgb[sl].float() / 256, "avail_actions": self._avail[sl],
+                "obs": e.obs_view()[sl].float() / 256, "agent_pos": e.agent_pos[sl].float(),
+                "agent_orientation": self._orient_vec[e.agent_orient[sl].long()]}
+
+    def _range_step(self, r, t, last, homophily, test_mode, Bg):
+        """One time step of one env range, in the call order of episode_runner.py:56-118."""
+        e, mac, sl, batch = self.env, self.mac, r["sl"], r["batch"]
+        self._give_hidden(r["hidden"])
+        if self.front is not None:
+            self.front.rows = (r["lo"] * e.n, Bg * e.n)
+        batch.update(self._pre_transition(sl), ts=t)
+        if homophily:
+            actions = mac.select_actions_env(batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+        else:
+            actions = mac.select_actions(batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+        if not last:
+            self._actions_u8[sl] = (actions % self.args.n_actions).reshape(Bg, e.n).to(device=e.device, dtype=torch.uint8)
+            if self.groups == 1:
+                e.step(self._actions_u8, want_state=True)
+            else:
+                e.step_range(self._actions_u8, r["lo"], Bg, want_state=True)
+            reward = e.reward[sl].float()
+            r["ret"] += reward
+            post = {"actions": actions, "reward": reward if getattr(self.args, "ind_reward", True) else reward.sum(1, keepdim=True),
+                    "terminated": e.done[sl].view(Bg, 1), "clean_num": e.clean[sl].float(),
+                    "apple_den": (e.apple_cnt[sl].to(torch.int32) & 0xFFFF).double().view(Bg, 1).expand(Bg, e.n) / e.G}
+            batch.update(post, ts=t)
+        if homophily:
+            actions_inc = mac.select_actions_inc(actions, batch, t_ep=t, t_env=self.t_env, test_mode=test_mode,
+                                                 agent_pos_replay=e.agent_pos[sl].float())
+            batch.update({"actions_inc": actions_inc}, ts=t)
+        if last:
+            batch.update({"actions": actions}, ts=t)
+        r["hidden"] = self._take_hidden()
 
     def run(self, test_mode=False):
         if getattr(self, "front", None) is not None:
@@ -108,48 +146,48 @@ class BatchedEpisodeRunner:
             if getattr(self, "front", None) is not None:
                 self.front.active = False
 
+    def _take_hidden(self):
+        return tuple(getattr(self.mac, k, None) for k in ("h_env", "h_inc"))
+
+    def _give_hidden(self, hidden):
+        for k, v in zip(("h_env", "h_inc"), hidden):
+            if v is not None:
+                setattr(self.mac, k, v)
+
     def _run(self, test_mode=False):
+        """One episode of all B envs.  With ``args.env_groups = G > 1`` the batch is rolled out as G independent env ranges,
+        each with its own MAC hidden state and CUDA stream (``SSDBatchEnv.step_range``): while the GPU steps and renders one
+        range, the host is already launching the policy of the next, and the logic phase of one range overlaps the
+        observation stores of another.  Trajectories do not depend on G (draws are keyed by the global env id)."""
         self.reset()
-        e, B = self.env, self.batch_size
-        terminated = False
-        episode_return = torch.zeros(B, e.n, device=e.device)
-        self.mac.init_hidden(batch_size=B)
-        if getattr(self.args, "mac", None) == "separate_mac":
-            self.mac.init_latent(batch_size=B)
+        e, B, G = self.env, self.batch_size, self.groups
+        Bg = B // G
         homophily = "homophily" in getattr(self.args, "name", "homophily")
-        env_info = {}
-        while not terminated:
-            self.batch.update(self._pre_transition(), ts=self.t)
-            if homophily:
-                actions = self.mac.select_actions_env(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
-            else:
-                actions = self.mac.select_actions(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
-            actions_env = actions % self.args.n_actions
-            e.step(actions_env.reshape(B, e.n).to(device=e.device, dtype=torch.uint8).contiguous(), want_state=True)
-            reward = e.reward.float()
-            episode_return += reward
-            # no host sync in the step loop: every env shares episode_limit and get_done() is constantly False in the
-            # reference (agent.py:192,243; map_env.py:890-894), so `terminated` is a host-side step count; the device-side
-            # `done` flags (what goes into the batch) are checked against it once per episode below
-            terminated = self.t + 1 >= self.episode_limit
-            post = {"actions": actions, "reward": reward if getattr(self.args, "ind_reward", True) else reward.sum(1, keepdim=True),
-                    "terminated": e.done.view(B, 1), "clean_num": e.clean.float(),
-                    "apple_den": (e.apple_cnt.to(torch.int32) & 0xFFFF).double().view(B, 1).expand(B, e.n) / e.G}
-            self.batch.update(post, ts=self.t)
-            if homophily:
-                actions_inc = self.mac.select_actions_inc(actions, self.batch, t_ep=self.t, t_env=self.t_env,
-                                                          test_mode=test_mode, agent_pos_replay=e.agent_pos.float())
-                self.batch.update({"actions_inc": actions_inc}, ts=self.t)
-            self.t += 1
-        self.batch.update(self._pre_transition(), ts=self.t)
-        if homophily:
-            actions = self.mac.select_actions_env(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
-            actions_inc = self.mac.select_actions_inc(actions, self.batch, t_ep=self.t, t_env=self.t_env,
-                                                      test_mode=test_mode, agent_pos_replay=e.agent_pos.float())
-            self.batch.update({"actions_inc": actions_inc}, ts=self.t)
-        else:
-            actions = self.mac.select_actions(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)
-        self.batch.update({"actions": actions}, ts=self.t)
+        if getattr(self.args, "mac", None) == "separate_mac":
+            self.mac.init_latent(batch_size=Bg)
+        main = torch.cuda.current_stream(e.device)
+        ranges = []
+        for k in range(G):
+            sl = slice(k * Bg, (k + 1) * Bg)
+            self.mac.init_hidden(batch_size=Bg)
+            ranges.append({"sl": sl, "lo": k * Bg, "batch": self.batch if G == 1 else self.batch[sl],
+                           "stream": main if G == 1 else self._streams[k], "hidden": self._take_hidden(),
+                           "ret": torch.zeros(Bg, e.n, device=e.device)})
+            if G > 1:
+                self._streams[k].wait_stream(main)
+        # no host sync in the step loop: every env shares episode_limit and get_done() is constantly False in the reference
+        # (agent.py:192,243; map_env.py:890-894), so termination is a host-side step count; the device-side `done` flags (what
+        # goes into the batch) are checked against it once per episode below
+        for t in range(self.episode_limit + 1):
+            self.t = t
+            for r in ranges:
+                with torch.cuda.stream(r["stream"]):
+                    self._range_step(r, t, t == self.episode_limit, homophily, test_mode, Bg)
+        if G > 1:
+            for k in range(G):
+                main.wait_stream(self._streams[k])
+        self.t = self.episode_limit
+        episode_return = torch.cat([r["ret"] for r in ranges], dim=0)
 
         # termination info of every env (map_env.py:897-912), accumulated like B single-env episodes
         if not bool(e.done.all().item()):                     # first host sync of the episode

@@ -78,6 +78,7 @@ class MacFrontEnd:
         self.module = mac.agent.conv_to_fc
         self.original = mac.agent.rgb_preprocess
         self.active = False
+        self.rows = None                                      # (first agent view, count) of the env range being rolled out
         self._fe, self._stamp = None, None
         mac.agent.rgb_preprocess = self
 
@@ -90,9 +91,12 @@ class MacFrontEnd:
         return self._fe
 
     def __call__(self, x):
-        if not self.active or x.shape[0] != self.env.B * self.env.n:      # learner path (autograd) / foreign batch: the module
+        first, count = self.rows if self.rows is not None else (0, self.env.B * self.env.n)
+        if not self.active or x.shape[0] != count:            # learner path (autograd) / foreign batch: the module
             return self.original(x)
-        return self._front_end().forward_env(self.env)
+        lay = self.env.layout
+        return self._front_end().forward(self.env.obs_buf.view(-1)[first * lay.obs_agent_stride:], count, lay.obs_agent_stride,
+                                         lay.obs_plane_stride, lay.obs_row_stride)
 
     def __deepcopy__(self, memo):
         """``copy.deepcopy(mac)`` (the learner's target network, homophily_learner.py:47) must not copy the kernel handle: the

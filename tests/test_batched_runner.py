@@ -29,6 +29,12 @@ class FakeBatch:
             self.data[k][bs, ts] = v.view_as(dest)
 
     def __getitem__(self, k):
+        if isinstance(k, slice):                              # EpisodeBatch[lo:hi]: a view on the same storage
+            view = FakeBatch.__new__(FakeBatch)
+            view.scheme, view.max_seq_length, view.device = self.scheme, self.max_seq_length, self.device
+            view.data = {name: t[k] for name, t in self.data.items()}
+            view.batch_size, view.offset = view.data["filled"].shape[0], k.start or 0
+            return view
         return self.data[k]
 
 
@@ -42,11 +48,13 @@ class ScriptedMAC:
         self.bs = batch_size
 
     def select_actions_env(self, batch, t_ep, t_env, test_mode=False):
-        return self.table[:, t_ep].clone()
+        lo = getattr(batch, "offset", 0)
+        return self.table[lo:lo + batch.batch_size, t_ep].clone()
 
     def select_actions_inc(self, actions, batch, t_ep, t_env, test_mode=False, agent_pos_replay=None):
         assert agent_pos_replay.shape[-1] == 2
-        return self.table_inc[:, t_ep].clone()
+        lo = getattr(batch, "offset", 0)
+        return self.table_inc[lo:lo + batch.batch_size, t_ep].clone()
 
 
 def _scheme(n, A, H, W, N):
@@ -56,8 +64,9 @@ def _scheme(n, A, H, W, N):
             "agent_pos": {"shape": (n, 2)}, "agent_orientation": {"shape": (n, 2)}, "actions_inc": {"shape": (n, n, 1), "dtype": torch.long}}
 
 
-@pytest.mark.parametrize("name,mp,n,view", [("cleanup", "default3", 3, 7), ("harvest", "default10", 5, 15)])
-def test_batched_runner_equals_sequential_facade_runs(name, mp, n, view):
+@pytest.mark.parametrize("name,mp,n,view,groups", [("cleanup", "default3", 3, 7, 1), ("harvest", "default10", 5, 15, 1),
+                                                    ("cleanup", "default3", 3, 7, 3)])
+def test_batched_runner_equals_sequential_facade_runs(name, mp, n, view, groups):
     from homophily_marl_b200.batched_runner import BatchedEpisodeRunner
     from homophily_marl_b200 import REGISTRY
     B, T = 6, 9
@@ -65,7 +74,7 @@ def test_batched_runner_equals_sequential_facade_runs(name, mp, n, view):
                  disable_fire_action=False, obs_color="full")
     env_args = dict(num_agents=n, render=False, episode_limit=T, is_replay=False, view_size=view, map=mp, extra_args=extra, seed=3)
     args = types.SimpleNamespace(batch_size_run=B, env=name, env_args=env_args, device="cuda:0", name="homophily", mac="homophily_mac",
-                                 n_actions=None, ind_reward=True, runner_log_interval=10 ** 9, test_nepisode=B)
+                                 n_actions=None, ind_reward=True, runner_log_interval=10 ** 9, test_nepisode=B, env_groups=groups)
     logged = {}
     logger = types.SimpleNamespace(log_stat=lambda k, v, t: logged.__setitem__(k, v))
     runner = BatchedEpisodeRunner(args, logger)

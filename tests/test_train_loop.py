@@ -123,7 +123,10 @@ def test_batched_runner_with_the_reference_episodebatch_mac_and_learner():
 
 def test_run_sequential_with_the_batched_runner():
     B = 64
+    # the whole B200 stack behind run_sequential: batched runner with 4 pipelined env ranges, fused u8 front end,
+    # device epsilon-greedy, DeviceHomophilyLearner; MAC, agent network and replay buffer are the reference's
     cfg = _cfg(runner="batched", batch_size_run=B, buffer_size=4 * B, batch_size=16, buffer_cpu_only=False,
+               env_groups=4, fused_frontend=True, action_selector="epsilon_greedy_b200", learner="homophily_learner_b200",
                t_max=3 * B * 100, test_nepisode=B, test_interval=2 * B * 100, log_interval=B * 100,
                runner_log_interval=B * 100, learner_log_interval=B * 100)
     r = refloop.run_training(cfg, backend="b200")
@@ -144,12 +147,12 @@ def test_batched_runner_with_fused_front_end_and_device_selector():
     from homophily_marl_b200.selectors import DeviceEpsilonGreedySelector
     assert isinstance(c.runner.front, MacFrontEnd) and isinstance(c.mac.action_selector, DeviceEpsilonGreedySelector)
     calls = {"fused": 0}
-    fwd = c.runner.front._front_end().forward_env
+    fwd = c.runner.front._front_end().forward
 
-    def counting(env, *a, **k):
+    def counting(*a, **k):
         calls["fused"] += 1
-        return fwd(env, *a, **k)
-    c.runner.front._front_end().forward_env = counting
+        return fwd(*a, **k)
+    c.runner.front._front_end().forward = counting
     batch = c.runner.run(test_mode=False)
     assert calls["fused"] == 21 and bool(batch["filled"].all())               # one per select_actions_env call (T + 1)
     # the fused features equal the module's on the stored fp32 observations (tolerance: tests/test_gpu_frontend.py)
