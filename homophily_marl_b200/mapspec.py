@@ -225,3 +225,18 @@ def compile_map(name: str, map_name: str, n_agents: int, view: int, episode_limi
                    base_grid=base, wall=wall.astype(np.uint8), apple_pts=apple, waste_pts=waste,
                    spawn_pts=spawn, thr_apple=thr_a, thr_waste=thr_w, thr_harvest=thr_h,
                    lut=color_lut(p.kind, obs_color))
+
+
+def dump_maps() -> str:
+    """The four shipped maps as plain ASCII (what the run-length rows above decode to), for auditing against
+    ``src/envs/ssd/constants.py``:  python -m homophily_marl_b200.mapspec"""
+    out = []
+    for key in _RLE:
+        rows = ascii_map(key)
+        out.append(f"{key}  {len(rows)}x{len(rows[0])}  sha {map_sha(rows)}")
+        out.extend("  |" + r + "|" for r in rows)
+    return "\n".join(out)
+
+
+if __name__ == "__main__":
+    print(dump_maps())

@@ -63,3 +63,17 @@ def test_errors_and_agent_chars():
     assert [mapspec.agent_char(i) for i in range(11)] == [1, 2, 3, 4, 5, 6, 7, 8, 9, 1, 1]
     for k, sha in mapspec.MAP_SHA.items():
         assert mapspec.map_sha(mapspec.ascii_map(k)) == sha
+
+
+def test_decoded_maps_equal_the_reference_constants_cell_for_cell():
+    """The run-length rows in mapspec.py decode to exactly the ASCII maps of src/envs/ssd/constants.py (dev container only)."""
+    from oracle import refshim
+    if not refshim.reference_available():
+        pytest.skip("/root/reference not present")
+    refshim._import_registry()
+    import envs.ssd.constants as C
+    from homophily_marl_b200 import mapspec
+    for key, ref in (("cleanup_n3", C.CLEANUP_N3_MAP), ("cleanup_n5", C.CLEANUP_N5_MAP), ("cleanup_n10", C.CLEANUP_N10_MAP),
+                     ("harvest_n10", C.HARVEST_N10_MAP)):
+        assert mapspec.ascii_map(key) == list(ref), key
+    assert "cleanup_n10  48x18" in mapspec.dump_maps()
