@@ -63,8 +63,10 @@ struct FrontParams {
     int N, P, RP, PS, AS, XB, n_chunks;      // obs geometry; chunks per tile = P * XB
     long long rows;
     int n_tiles;
+    int split;                               // a tile's chunks are divided among `split` work items (split-K) for load balance
     const uint8_t* obs;
     float* out;
+    float* scratch;                          // [split][rows][32] partial sums when split > 1 (finalised by a second kernel)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,6 +88,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {   // single-lane roles: poll, sleep, poll ...
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep(64);                     // leave the issue slots to the producer warps
+    }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -112,6 +123,14 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
     return r;
 }
 
+// u8 -> f32 on the full-rate pipes: 0x4B0000bb is the float 8388608 + bb (one PRMT), minus 8388608 (one FADD); I2F is a
+// quarter-rate conversion-pipe instruction and 90 of them per 1296 FFMAs showed up in the profile
+__device__ __forceinline__ float byte_to_float(uint32_t word, int b) {
+    uint32_t v;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(word), "r"(0x4B000000u), "r"(0x7540u + (uint32_t)b));
+    return __uint_as_float(v) - 8388608.0f;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ CUtensorMap wmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -134,38 +153,55 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t smem_base = smem_u32(smem);
-    const int stages_per_tile = p.n_chunks * kOC;
+    const int n_items = p.n_tiles * p.split;
 
     if (warp < 8) {
         // ------------------------------------------------------------------ producers (+ epilogue on warps 0-3)
         const int r = tid & 127, strip = tid >> 7;             // GEMM row within the tile; 8-pixel half of the 16-pixel block
-        uint32_t it = 0, tile_n = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_n) {
+        uint32_t it = 0, item_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+            const int tile = item / p.split, part = item - tile * p.split;
+            const int c_begin = part * p.n_chunks / p.split, c_end = (part + 1) * p.n_chunks / p.split;
+            const int stages_here = (c_end - c_begin) * kOC;
             const long long row = (long long)tile * kTileM + r;
+            // The 27 words of the NEXT chunk's patch are requested before the current chunk is convolved, so their L2 latency is
+            // hidden behind 1 296 FFMAs.  (A shared-memory row window filled with coalesced loads was measured and dropped: the
+            // per-row CTA barrier cost more than the sectors it saved -- V=15: 515 us instead of 397 us, profiles/r2_notes.md.)
             const long long row_ld = row < p.rows ? row : p.rows - 1;          // partial last tile: compute on a valid row, never store
             const uint8_t* view = p.obs + row_ld * p.AS;
-            for (int c = 0; c < p.n_chunks; ++c) {
-                const int y = c / p.XB, xb = c - y * p.XB;
-                const int x0 = xb * 16 + strip * 8;
-                // patch[ch][dy][0..9] as floats: raw bytes (the 1/256 lives in the conv weights)
-                float patch[3][3][10];
+            uint32_t nxt[27];
+            auto request = [&](int c) {
+                const int y = c / p.XB, xb = c - y * p.XB, x0 = xb * 16 + strip * 8;
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         const uint8_t* src = view + ch * p.PS + (y + dy) * p.RP + x0;
-                        uint32_t w0 = 0, w1 = 0, w2 = 0;
-                        if (x0 < p.RP) w0 = __ldg(reinterpret_cast<const uint32_t*>(src));
-                        if (x0 + 4 < p.RP) w1 = __ldg(reinterpret_cast<const uint32_t*>(src + 4));
-                        if (x0 + 8 < p.N) w2 = __ldg(reinterpret_cast<const uint32_t*>(src + 8));   // only pixels x0+8, x0+9 < N are used
+                        const int k = (ch * 3 + dy) * 3;
+                        nxt[k] = x0 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
+                        nxt[k + 1] = x0 + 4 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src + 4)) : 0u;
+                        nxt[k + 2] = x0 + 8 < p.N ? __ldg(reinterpret_cast<const uint32_t*>(src + 8)) : 0u;   // only pixels x0+8, x0+9 < N are used
+                    }
+            };
+            request(c_begin);
+            for (int c = c_begin; c < c_end; ++c) {
+                // patch[ch][dy][0..9] as floats: raw bytes (the 1/256 lives in the conv weights).  Pixels beyond the image row are
+                // finite garbage (the next row / zeros) that only meets zero FC weights.
+                float patch[3][3][10];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const int k = (ch * 3 + dy) * 3;
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
-                            patch[ch][dy][b] = (float)((w0 >> (8 * b)) & 0xffu);
-                            patch[ch][dy][4 + b] = (float)((w1 >> (8 * b)) & 0xffu);
+                            patch[ch][dy][b] = byte_to_float(nxt[k], b);
+                            patch[ch][dy][4 + b] = byte_to_float(nxt[k + 1], b);
                         }
-                        patch[ch][dy][8] = (float)(w2 & 0xffu);
-                        patch[ch][dy][9] = (float)((w2 >> 8) & 0xffu);
+                        patch[ch][dy][8] = byte_to_float(nxt[k + 2], 0);
+                        patch[ch][dy][9] = byte_to_float(nxt[k + 2], 1);
                     }
+                if (c + 1 < c_end) request(c + 1);
 #pragma unroll
                 for (int oc = 0; oc < kOC; ++oc, ++it) {
                     float acc[8];
@@ -183,11 +219,10 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                             }
                     uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int px = 0; px < 8; ++px) {
-                        float a = leaky(acc[px], p.slope);
-                        if (x0 + px >= p.P) a = 0.f;                          // padding pixel of the 16-pixel block
+                    for (int px = 0; px < 8; ++px) {                           // (padding pixels meet zero weights: no masking)
+                        const float a = fmaxf(acc[px], acc[px] * p.slope);     // LeakyReLU for 0 <= slope <= 1 (checked at create)
                         hi[px] = to_tf32(a);                                   // round-to-nearest tf32: exactly what the tensor core will read
-                        lo[px] = to_tf32(a - __uint_as_float(hi[px]));         // a - hi is exact in fp32; |lo| <= 2^-11 |a|
+                        lo[px] = __float_as_uint(a - __uint_as_float(hi[px])); // exact in fp32, |lo| <= 2^-11 |a|; the tensor core keeps its top 10 bits
                     }
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);               // the MMAs that read this slot have completed
@@ -203,14 +238,14 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
             }
             if (warp < 4) {
                 // -------------------------------------------------------------- epilogue: TMEM lane = GEMM row = r
-                mbar_wait(smem_u32(&bar_tmem_full), tile_n & 1u);
+                mbar_wait(smem_u32(&bar_tmem_full), item_n & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float sum[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sum[j] = 0.f;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
                 // the partial sums are added smallest first (accumulator 0 holds the lo terms), in fp32 round-to-nearest
-                const int n_acc = min(kAccs, 1 + stages_per_tile * (kStageK / 8));   // tiny views use fewer than 16
+                const int n_acc = min(kAccs, 1 + stages_here * (kStageK / 8));       // short items use fewer than 16
                 for (int a = 0; a < n_acc; ++a) {
                     uint32_t v[32];
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -227,7 +262,11 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(smem_u32(&bar_tmem_empty));                        // the accumulator may be overwritten by the next tile
-                if (row < p.rows) {
+                if (row < p.rows && p.split > 1) {                              // partial sums; bias and activation in finalize
+                    float4* dst = reinterpret_cast<float4*>(p.scratch + ((long long)part * p.rows + row) * kFeat);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
+                } else if (row < p.rows) {
                     float4* dst = reinterpret_cast<float4*>(p.out + row * kFeat);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -245,14 +284,16 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
         // ---------------------------------------------------------------------- MMA issuer (one elected lane)
         // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 32, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kFeat >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-        uint32_t it = 0, tile_n = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_n) {
-            if (tile_n > 0) mbar_wait(smem_u32(&bar_tmem_empty), (tile_n - 1) & 1u);   // the epilogue has drained the previous tile
+        uint32_t it = 0, item_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+            const int tile = item / p.split, part = item - tile * p.split;
+            const int stages_here = ((part + 1) * p.n_chunks / p.split - part * p.n_chunks / p.split) * kOC;
+            if (item_n > 0) mbar_wait_relaxed(smem_u32(&bar_tmem_empty), (item_n - 1) & 1u);   // the epilogue has drained the previous item
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t used = 0;                                                 // accumulators already written in this tile
-            for (int st = 0; st < stages_per_tile; ++st, ++it) {
+            uint32_t used = 0;                                                 // accumulators already written in this item
+            for (int st = 0; st < stages_here; ++st, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-                mbar_wait(smem_u32(&bar_full[s]), ph);                         // A written by 256 producers, B landed by TMA
+                mbar_wait_relaxed(smem_u32(&bar_full[s]), ph);                 // A written by 256 producers, B landed by TMA
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t a_hi = smem_base + s * kStageBytes, a_lo = a_hi + kABytes;
@@ -271,7 +312,7 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                         used |= 1u | (1u << acc);
                     }
                     umma_commit(smem_u32(&bar_empty[s]));                      // frees the slot when these MMAs have read it
-                    if (st == stages_per_tile - 1) umma_commit(smem_u32(&bar_tmem_full));
+                    if (st == stages_here - 1) umma_commit(smem_u32(&bar_tmem_full));
                 }
                 __syncwarp();
             }
@@ -280,20 +321,39 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
         // ---------------------------------------------------------------------- TMA: FC weight tile of every stage
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
-                for (int st = 0; st < stages_per_tile; ++st, ++it) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int part = item % p.split;
+                const int st_begin = (part * p.n_chunks / p.split) * kOC, st_end = ((part + 1) * p.n_chunks / p.split) * kOC;
+                for (int st = st_begin; st < st_end; ++st, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                    mbar_wait_relaxed(smem_u32(&bar_empty[s]), ph ^ 1u);
                     const uint32_t full = smem_u32(&bar_full[s]);
                     mbar_arrive_expect_tx(full, 2 * kBBytes);
                     tma_load_2d(smem_base + s * kStageBytes + 2 * kABytes, &wmap, full, 0, st * 4);   // 4 rows of 256 floats = hi + lo
                 }
+            }
         }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(kTmemCols) : "memory");
+}
+
+// split-K epilogue: out = LeakyReLU(bias + sum over parts, in part order), one thread per output float4
+__global__ void frontend_finalize_kernel(const float* __restrict__ scratch, float* __restrict__ out, long long rows, int split,
+                                         const __grid_constant__ FrontParams p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
+    if (i >= rows * (kFeat / 4)) return;
+    const int j = (int)(i % (kFeat / 4)) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < split; ++s) {
+        const float4 v = reinterpret_cast<const float4*>(scratch + (long long)s * rows * kFeat)[i];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x = leaky(acc.x + p.fc_b[j], p.slope); acc.y = leaky(acc.y + p.fc_b[j + 1], p.slope);
+    acc.z = leaky(acc.z + p.fc_b[j + 2], p.slope); acc.w = leaky(acc.w + p.fc_b[j + 3], p.slope);
+    reinterpret_cast<float4*>(out)[i] = acc;
 }
 
 thread_local int g_front_cuda_error = 0;
@@ -311,6 +371,8 @@ struct ssd_frontend {
     FrontParams fp;
     CUtensorMap wmap;
     float* d_w;                                                // packed FC weights: [stages][hi 512 | lo 512] floats
+    float* d_scratch;                                          // split-K partial sums, grown on demand
+    size_t scratch_floats;
     int device, view, sms;
     size_t smem_bytes;
 };
@@ -322,6 +384,7 @@ int ssd_frontend_create(int32_t view, const float* conv_w, const float* conv_b, 
     if (!out) return SSD_ERR_INVALID;
     *out = nullptr;
     if (!conv_w || !conv_b || !fc_w || !fc_b || view < 1 || view > 31) return SSD_ERR_INVALID;
+    if (!(negative_slope >= 0.0f && negative_slope <= 1.0f)) return SSD_ERR_INVALID;              // LeakyReLU as max(x, slope x)
     const int N = 2 * view + 1, P = N - 2, XB = (P + 15) / 16, n_chunks = P * XB, stages = n_chunks * kOC;
     ssd_frontend* f = new (std::nothrow) ssd_frontend;
     if (!f) return SSD_ERR_INVALID;
@@ -402,13 +465,46 @@ int ssd_frontend_forward(ssd_frontend* f, const uint8_t* obs, int64_t rows, int3
     p.RP = obs_row_stride; p.PS = obs_plane_stride; p.AS = obs_agent_stride;
     p.rows = rows; p.n_tiles = (int)((rows + kTileM - 1) / kTileM);
     p.obs = obs; p.out = out;
+    // split-K for load balance: 160 tiles on 148 persistent CTAs would leave a second, almost empty round.  A tile's chunks are
+    // divided among `split` work items; the factor minimises rounds x (chunks per item + ~1.5 chunks of pipeline fill and
+    // epilogue per item), which reproduces the measured optimum (profiles/r2_notes.md).  Partial sums are combined in part order
+    // by frontend_finalize_kernel, so the result does not depend on the schedule.
+    int split = 1;
+    {
+        double best = 1e30;
+        const int smax = p.n_chunks < 16 ? p.n_chunks : 16;
+        for (int s_ = 1; s_ <= smax; ++s_) {
+            const long long items = (long long)p.n_tiles * s_;
+            const double rounds = (double)((items + f->sms - 1) / f->sms);
+            const double cost = rounds * ((double)p.n_chunks / s_ + 1.5);
+            if (cost < best - 1e-9) { best = cost; split = s_; }
+        }
+    }
+    { const char* e_ = getenv("SSD_B200_FRONTEND_SPLIT"); if (e_ && atoi(e_) >= 1 && atoi(e_) <= p.n_chunks) split = atoi(e_); }   // tuning
+    p.split = split;
     int prev = -1;
     cudaError_t e = cudaGetDevice(&prev);
     if (e == cudaSuccess && prev != f->device) e = cudaSetDevice(f->device);
+    if (e == cudaSuccess && split > 1) {
+        const size_t need = (size_t)split * (size_t)rows * kFeat;
+        if (need > f->scratch_floats) {                        // first call / larger batch: (re)allocate (not capturable)
+            if (f->d_scratch) cudaFree(f->d_scratch);
+            f->d_scratch = nullptr; f->scratch_floats = 0;
+            e = cudaMalloc(&f->d_scratch, need * sizeof(float));
+            if (e == cudaSuccess) f->scratch_floats = need;
+        }
+        p.scratch = f->d_scratch;
+    }
     if (e == cudaSuccess) {
-        const int grid = p.n_tiles < f->sms ? p.n_tiles : f->sms;
+        const int items = p.n_tiles * split;
+        const int grid = items < f->sms ? items : f->sms;
         obs_frontend_kernel<<<grid, kThreads, f->smem_bytes, (cudaStream_t)stream>>>(p, f->wmap);
         e = cudaGetLastError();
+        if (e == cudaSuccess && split > 1) {
+            const long long n4 = rows * (kFeat / 4);
+            frontend_finalize_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.scratch, out, rows, split, p);
+            e = cudaGetLastError();
+        }
     }
     if (prev >= 0 && prev != f->device) cudaSetDevice(prev);
     if (e != cudaSuccess) { g_front_cuda_error = (int)e; return SSD_ERR_CUDA; }
@@ -421,6 +517,7 @@ int ssd_frontend_destroy(ssd_frontend* f) {
     cudaGetDevice(&prev);
     if (prev != f->device) cudaSetDevice(f->device);
     cudaFree(f->d_w);
+    if (f->d_scratch) cudaFree(f->d_scratch);
     if (prev >= 0 && prev != f->device) cudaSetDevice(prev);
     delete f;
     return SSD_OK;

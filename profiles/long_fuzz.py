@@ -36,9 +36,12 @@ for key in ("cleanup5", "cleanup10_full", "cleanup3", "harvest5", "harvest10_ful
         assert np.array_equal(env.reward.cpu().numpy(), out["reward"]), (key, t, "reward")
         assert np.array_equal(env.clean.cpu().numpy(), out["clean"]), (key, t, "clean")
         assert np.array_equal(env.obs_view().cpu().numpy(), out["obs"]), (key, t, "obs")
+        assert np.array_equal(env.apple_cnt.cpu().numpy().view(np.uint16), out["apple_cnt"]), (key, t, "apple_cnt")
         if t % 10 == 0:
             assert np.array_equal(env.grid.cpu().numpy(), ora.grid), (key, t, "grid")
             assert np.array_equal(env.agent_pos.cpu().numpy(), ora.pos_rc), (key, t, "pos")
+            g = env.grid_buf[:, :env.G]                     # the running cell counts equal a recount of the grid
+            assert torch.equal(env.counts_buf, ((g == 2).sum(1) | ((g == 3).sum(1) << 16)).to(torch.int32)), (key, t, "counts")
         if out["done"].all():
             env.reset(); ora.reset(threads=16)
     assert int(ora.envs["error"].sum()) == 0
