@@ -297,6 +297,59 @@ def train_e2e(a, which=("b200", "b200_batched", "reference")):
     return out
 
 
+# --------------------------------------------------------------------------- policy-side kernel
+def frontend_probe(cfg, a, dev):
+    """Fused u8-obs front end (conv3x3 + LeakyReLU on CUDA cores -> Linear on tcgen05) on the observations of the headline
+    workload, next to the torch module it replaces (u8 -> fp32 /256 -> Conv2d -> Linear).  Bound: the conv's fp32 FMAs."""
+    import torch
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    from homophily_marl_b200.frontend import ObsFrontEnd
+    B, n, view = cfg["envs_per_gpu"], cfg["num_agents"], cfg["view_size"]
+    env = SSDBatchEnv(cfg["env"], B, n, map=cfg["map"], view_size=view, episode_limit=LIMIT, extra_args=extra_args(a), seed=a.seed, device=dev)
+    env.reset()
+    P = 2 * view - 1
+    torch.manual_seed(a.seed)
+    mod = torch.nn.Sequential(torch.nn.Conv2d(3, 6, 3, 1), torch.nn.LeakyReLU(), torch.nn.Flatten(),
+                              torch.nn.Linear(6 * P * P, 32), torch.nn.LeakyReLU()).to(dev)
+    fe = ObsFrontEnd.from_module(mod, view, device=dev)
+    x8 = env.obs_view().reshape(B * n, 3, env.N, env.N)
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+    with torch.no_grad():
+        t_fused = timed(lambda: fe.forward_env(env))
+        t_torch = timed(lambda: mod(x8.float() / 256))
+        err = float((fe.forward_env(env) - mod(x8.float() / 256)).abs().max())
+    rows = B * n
+    conv_flop = rows * 6 * P * P * 27 * 2
+    fc_flop = rows * 6 * P * P * 32 * 2
+    sm_mhz = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1965.0
+    fp32_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fe.close()
+    env.close()
+    return {"what": "ssd_frontend_forward on the workload's u8 observations: conv3x3(3->6)+LeakyReLU -> Linear(->32)+LeakyReLU",
+            "agent_views": rows, "us": t_fused * 1e6, "views_per_s": rows / t_fused,
+            "torch_module_us": t_torch * 1e6, "speedup_vs_torch": t_torch / t_fused, "max_abs_diff_vs_torch_default": err,
+            "roofline": {"bound": "fp32 FMA on the CUDA cores (conv); the tcgen05 Linear and HBM are far from their limits",
+                         "conv_tflops": conv_flop / t_fused / 1e12, "fp32_peak_tflops": fp32_peak,
+                         "frac": conv_flop / t_fused / 1e12 / fp32_peak, "fc_tensor_tflops_3x_tf32": 3 * fc_flop / t_fused / 1e12,
+                         "hbm_gbs": rows * env_bytes_per_view(view) / t_fused / 1e9}}
+
+
+def env_bytes_per_view(view):
+    N = 2 * view + 1
+    return 3 * N * ((N + 3) // 4 * 4) + 32 * 4
+
+
 # --------------------------------------------------------------------------- CUDA arm
 def ring_len(obs_bytes, forced=0):
     """Observation ring > 2.2 x L2, rounded up to a divisor of the episode length so the launch schedule has period LIMIT."""
@@ -600,6 +653,11 @@ def run_b200(a):
                                                         "sample": r1["sample"] + " -- the reference's only execution mode"}
             else:
                 line["cpu_baseline"] = port
+        if world == 1 and not a.no_extra:
+            try:
+                line["frontend"] = frontend_probe(cfg, a, dev)
+            except Exception as e:
+                line["frontend"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not a.no_train:
             line["train_e2e"] = train_e2e(a)
         print(json.dumps(line), flush=True)

@@ -113,7 +113,7 @@ __host__ __device__ constexpr GeoVals make_geo(int kind, int H, int W, int V) {
     g.off0 = 16; g.off1 = 16; g.off2 = 16 + szT; g.off3 = 16 + szT;        // by orientation: LEFT/RIGHT -> MT, UP/DOWN -> M
     g.PMS = szT + szM + 32;
     g.direct = g.RP <= 16;
-    g.padF = g.direct ? cround_up(V * W + 16, 16) : 16;
+    g.padF = g.direct ? cround_up(V * W + 48, 16) : 16;      // + 32 bytes at the very front for the (class, rank) -> lane table
     g.padB = g.direct ? cround_up(V * W + 32, 16) : 32;
     if (g.direct) g.PMS = 0;
     return g;
@@ -665,29 +665,29 @@ __device__ __forceinline__ void fill_outside(const SW& w, const GEO& g, const KP
 // index 6, reverses the run for DOWN / RIGHT, and colours 4 pixels per PRMT as the map path does.  No padded maps are built.
 // The grid tile has V rows of slack on both sides (zeroed at kernel start), so no load needs a bounds test; agents were
 // written into the staged grid as index 7 by the caller.
-template <class SW, class GEO>
-__device__ __forceinline__ void gather_direct(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* gobs, int lane,
-                                              bool is_agent, int r0, int c0, int ori) {
-    const int N = g.N(), V = g.V(), W = g.W(), units = p.n * N, WR = g.RP() >> 2;
-    const uint32_t apack = (uint32_t)r0 | ((uint32_t)c0 << 8) | ((uint32_t)ori << 16);
+template <bool COLS, class SW, class GEO>
+__device__ __forceinline__ void gather_class(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, const uint8_t* rank2lane,
+                                             uint8_t* gobs, int lane, uint32_t apack, int n_in_class) {
+    const int N = g.N(), V = g.V(), W = g.W(), units = n_in_class * N, WR = g.RP() >> 2;
     const uint32_t lastmask = 0xffffffffu >> (8 * (4 * WR - N));
     for (int u0 = 0; u0 < units; u0 += SW::kLanes) {
         const int u = u0 + lane;
         const bool valid = u < units;
-        const int al = valid ? g.divN(u) : 0;
-        const int y = u - al * N;
+        const int rank = valid ? g.divN(u) : 0;
+        const int y = u - rank * N;
+        const int al = rank2lane[rank];
         const uint32_t ap = w.shfl(apack, al);
         if (!valid) continue;
         const int ar = (int)(ap & 0xffu), ac = (int)((ap >> 8) & 0xffu), o = (int)(ap >> 16);
         uint32_t b0, b1, b2, b3;                              // element i of the run (ascending map coordinate) in byte i
         int lo, hi;                                           // elements inside the map: [lo, hi)
-        if (o >= 2) {                                         // UP / DOWN: a run along map row R
+        if (!COLS) {                                          // UP / DOWN: a run along map row R
             const int R = o == 2 ? ar - V + y : ar + V - y;
             const bool rv = (unsigned)R < (unsigned)g.H();
             lo = rv ? max(0, V - ac) : 0;
             hi = rv ? min(N, W + V - ac) : 0;
             const int start = (rv ? R : 0) * W + ac - V;      // >= -V: inside the front slack
-            SSD_CHECK(start >= -g.padF() && start + 20 <= g.GS() + g.padB());
+            SSD_CHECK(start >= -g.padF() + 32 && start + 20 <= g.GS() + g.padB());
             const uint32_t* wp = reinterpret_cast<const uint32_t*>(sg + (start & ~3));
             const uint32_t sh = (uint32_t)(start & 3) * 8u;
             const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
@@ -699,7 +699,7 @@ __device__ __forceinline__ void gather_direct(const SW& w, const GEO& g, const K
             lo = cv ? max(0, V - ar) : 0;
             hi = cv ? min(N, g.H() + V - ar) : 0;
             const uint8_t* col = sg + (ar - V) * W + (cv ? C : 0);     // rows ar-V .. ar+V: at most V rows into either slack
-            SSD_CHECK((ar - V) * W >= -g.padF() && (ar + V) * W + W <= g.GS() + g.padB());
+            SSD_CHECK((ar - V) * W >= -g.padF() + 32 && (ar + V) * W + W <= g.GS() + g.padB());
             uint32_t e[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) e[i] = i < N ? (uint32_t)col[i * W] : 0u;
@@ -739,6 +739,23 @@ __device__ __forceinline__ void gather_direct(const SW& w, const GEO& g, const K
     }
 }
 
+// The rows of UP / DOWN agents and of LEFT / RIGHT agents are gathered in two separate passes, so that a trip of the warp runs
+// ONE of the two load schemes instead of both under divergence.  `tbl` (32 bytes at the very start of the tile's front slack,
+// never touched by a gather load) maps (class, rank within class) -> agent lane.
+template <class SW, class GEO>
+__device__ __forceinline__ void gather_direct(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* tbl, uint8_t* gobs, int lane,
+                                              bool is_agent, int r0, int c0, int ori) {
+    const uint32_t apack = (uint32_t)r0 | ((uint32_t)c0 << 8) | ((uint32_t)ori << 16);
+    const unsigned m_rows = w.ballot(is_agent && ori >= 2), m_cols = w.ballot(is_agent && ori < 2);
+    if (is_agent) {
+        const bool cols = ori < 2;
+        tbl[(cols ? 16 : 0) + __popc((cols ? m_cols : m_rows) & ((1u << lane) - 1u))] = (uint8_t)lane;
+    }
+    w.sync();
+    if (m_rows) gather_class<false>(w, g, p, sg, tbl, gobs, lane, apack, __popc(m_rows));
+    if (m_cols) gather_class<true>(w, g, p, sg, tbl + 16, gobs, lane, apack, __popc(m_cols));
+}
+
 template <class SW, class GEO>
 __device__ __forceinline__ void render(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
                                        int lane, bool is_agent, int pos, int ori, int env) {
@@ -763,7 +780,7 @@ __device__ __forceinline__ void render(const SW& w, const GEO& g, const KParams&
     uint8_t* gobs = p.obs + (size_t)env * (p.n * g.AS());
 
     if (g.direct()) {
-        gather_direct(w, g, p, sg, gobs, lane, is_agent, r0, c0, ori);
+        gather_direct(w, g, p, sg, const_cast<uint8_t*>(sg) - g.padF(), gobs, lane, is_agent, r0, c0, ori);
     } else {
         // the maps were pre-filled with "outside the map" at kernel start (fill_outside); now the cells (agents are already in
         // the staged grid as index 7)

@@ -41,7 +41,7 @@ for r in first:
     parts = r[src].split()
     op = parts[1] if parts[0].startswith("@") else parts[0]
     c[op] += int(r[ie]); s[op] += int(r[smp])
-for op, v in c.most_common(18):
+for op, v in c.most_common(70):
     print("  %-22s %8.1f /env-step   samples %d" % (op, v / n_env, s[op]))
 
 # per source line (correlated view)

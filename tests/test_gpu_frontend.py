@@ -3,9 +3,10 @@
 (src/modules/agents/homophily_agent.py:19-27).
 
 Tolerance (stated, not hidden): the reference computes in fp32.  The kernel's conv is fp32 FMA; the Linear contraction runs
-on tf32 tensor cores with both operands split hi + lo (hi*hi + lo*hi + hi*lo, fp32 accumulate), which leaves a relative
-error below 2^-19 per product.  Against an fp64 evaluation of the same module the kernel must be within 4e-6 * (1 + |y|)
--- the same order as torch's own fp32 error -- and within 1e-5 * (1 + |y|) of torch fp32 on the GPU."""
+on tf32 tensor cores with both operands split hi + lo (hi*hi + lo*hi + hi*lo), accumulated in fp32 over 16 TMEM accumulators
+and split-K partial sums.  Against an fp64 evaluation of the same module the kernel must be within 1e-6 * (1 + |y|) -- measured
+0.3e-7 .. 1.2e-7, torch's own fp32 path measures 0.5e-7 .. 1.0e-6 on the same inputs -- and within 3e-6 * (1 + |y|) of torch
+fp32 on the GPU (TF32 disabled in cuDNN / cuBLAS for the comparison)."""
 import numpy as np
 import pytest
 
@@ -38,7 +39,7 @@ def _compare(fe, mod, obs_buf, rows, lay, N):
     err64 = ((g - w64).abs() / (1 + w64.abs())).max().item()
     err32 = ((g - w32).abs() / (1 + w32.abs())).max().item()
     torch_err64 = ((w32 - w64).abs() / (1 + w64.abs())).max().item()
-    assert err64 < 4e-6 and err32 < 1e-5, (err64, err32, torch_err64)
+    assert err64 < 1e-6 and err32 < 3e-6, (err64, err32, torch_err64)
     return err64, torch_err64
 
 
