@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--replays", type=int, default=0, help="timed replays of the K-step schedule (0 = auto, >= 5)")
     ap.add_argument("--groups", type=int, default=0,
                     help="step the batch as G independent env ranges on G streams (SSDBatchEnv.step_range, the asynchronous-sampler "
-                         "API BatchedEpisodeRunner uses with args.env_groups); 0 = auto: 4 for single-wave batches (<= 8192 envs), else 1")
+                         "API BatchedEpisodeRunner uses with args.env_groups); 0 = auto: 8 ranges for <= 4096 envs, 4 for <= 8192, else 1")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--random-spawn", action="store_true")
@@ -250,7 +250,7 @@ def train_e2e(a, which=("b200", "b200_batched", "reference")):
     """`run.run_sequential` of the UNCHANGED reference (rollouts + replay + HomophilyLearner updates + test episodes),
     Cleanup default3 / 3 agents / yaml hyper-parameters, t_max env steps: on the CUDA env through the reference's own
     single-env EpisodeRunner ('b200'), through BatchedEpisodeRunner at B=256 with the fused u8 front end, the device epsilon-greedy
-    selector and DeviceHomophilyLearner ('b200_batched', 20 x t_max env steps; MAC and replay buffer are the reference's), and on
+    selector and DeviceHomophilyLearner ('b200_batched', 100 x t_max env steps; MAC and replay buffer are the reference's), and on
     the reference's own CPU env ('reference').  env-steps/s = train env steps / wall seconds (test episodes are extra work)."""
     from baseline import refloop
     out = {"what": "run_sequential, Cleanup default3, 3 agents, homophily IQL, yaml defaults; env-steps/s incl. learner updates + tests",
@@ -275,7 +275,13 @@ def train_e2e(a, which=("b200", "b200_batched", "reference")):
         try:
             if key == "b200_batched":
                 B = 256
-                t_max = 20 * a.train_t_max
+                t_max = 100 * a.train_t_max                                # 10 rollouts of 256 episodes + 10 learner steps
+                if cuda:                                                   # untimed: the batched stack's own kernels / cuDNN shapes
+                    wcfg = refloop.load_config("cleanup", t_max=1, runner="batched", batch_size_run=B, buffer_size=2 * B,
+                                               buffer_cpu_only=False, fused_frontend=True, action_selector="epsilon_greedy_b200",
+                                               learner="homophily_learner_b200",
+                                               **{**common, "test_nepisode": B, "test_interval": 10 ** 9})
+                    refloop.run_training(wcfg, backend="b200")
                 cfg = refloop.load_config("cleanup", t_max=t_max, runner="batched", batch_size_run=B, buffer_size=4 * B,
                                           buffer_cpu_only=False, fused_frontend=True, action_selector="epsilon_greedy_b200",
                                           learner="homophily_learner_b200",
@@ -538,7 +544,7 @@ def run_b200(a):
     B, n = cfg["envs_per_gpu"], cfg["num_agents"]
     K, R = a.steps, auto_replays(a, a.steps)
     if a.groups <= 0:                                         # one wave of warps cannot overlap its own logic and store phases
-        a.groups = 4 if (B <= 8192 and B % 4 == 0) else 1
+        a.groups = 8 if (B <= 4096 and B % 8 == 0) else (4 if (B <= 8192 and B % 4 == 0) else 1)
     single = None
     if a.groups > 1:                                          # the same K steps as ONE launch per step, for the record
         r1, ro1 = measure(cfg, a, dev, rank, world, K, a.warmup, max(5, R // 4), groups=1, dist=dist)

@@ -211,13 +211,23 @@ class SSDBatchEnv:
                                 (self.obs_buf if obs_out is None else obs_out).data_ptr() if want_obs else None,
                                 self.state_rgb.data_ptr() if (want_state and self.state_rgb is not None) else None)
 
-    def step(self, actions, draws=None, obs_out=None, want_obs=True, want_state=False):
-        """actions: u8 CUDA tensor [B, n].  Results land in self.reward / clean / apple_cnt / done / obs."""
+    def step(self, actions, draws=None, obs_out=None, want_obs=True, want_state=False, auto_reset=False):
+        """actions: u8 CUDA tensor [B, n].  Results land in self.reward / clean / apple_cnt / done / obs.
+
+        ``auto_reset=True``: every env whose ``done`` flag this step raised is reset by a masked ``ssd_reset`` launch on the same
+        stream (no host sync), and its slot of the observation buffer then holds the FIRST observation of the new episode;
+        ``done`` / ``reward`` keep the values of the finished step.  Envs may therefore run on different episode clocks
+        (``load_state(t=...)``), which the reference -- one env, ``get_done()`` constantly False -- never needs."""
         self._check_actions(actions)
         d = self._draws(draws)
         so = self._step_out(obs_out, want_obs, want_state)
         _capi.check(self.lib.ssd_step(self._h, C.byref(self._st), _ptr(actions), C.byref(d) if d else None,
                                       C.byref(so), self._stream()))
+        if auto_reset:
+            out = None if not want_obs else (self.obs_buf if obs_out is None else obs_out)
+            _capi.check(self.lib.ssd_reset(self._h, C.byref(self._st), _ptr(self.done), None, _ptr(out), self._stream()))
+            if want_state and self.state_rgb is not None:
+                self.render(want_obs=False, want_state=True)
 
     def step_range(self, actions, env_begin, env_count, draws=None, obs_out=None, want_obs=True, want_state=False):
         """``step`` restricted to envs [env_begin, env_begin + env_count) (``ssd_step_range``).  ``actions`` is the

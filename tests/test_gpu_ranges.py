@@ -83,3 +83,33 @@ def test_check_actions_raises_keyerror_like_the_reference():
         env.step(bad)
     with pytest.raises(KeyError):
         env.step_range(bad, 0, 4)
+
+
+def test_masked_auto_reset_with_envs_on_different_episode_clocks():
+    """step(auto_reset=True): envs whose episode ends this step are reset in place (masked ssd_reset on the same stream) and
+    continue with a fresh episode while the others carry on -- checked against per-env oracle resets."""
+    from homophily_marl_b200.batch_env import SSDBatchEnv
+    B, n, limit = 48, 5, 9
+    extra = dict(random_spawn_point=True, random_spawn_rotation=None)
+    env = SSDBatchEnv("cleanup", B, n, map="default5", view_size=7, episode_limit=limit, extra_args=extra, seed=21, want_state=True)
+    ora = O.OracleBatch.from_spec(env.spec, n_envs=B, seed=21, random_spawn_point=True, spawn_rotation=None)
+    env.reset()
+    ora.reset()
+    t0 = np.arange(B, dtype=np.int32) % limit                   # staggered episode clocks
+    env.load_state(t=t0)
+    ora.envs["t"][:] = t0
+    rs = np.random.RandomState(4)
+    n_resets = 0
+    for t in range(3 * limit):
+        act = rs.randint(0, env.n_actions, size=(B, n)).astype(np.uint8)
+        env.step(torch.as_tensor(act, device=env.device), auto_reset=True, want_state=True)
+        out = ora.step(act)
+        assert np.array_equal(env.done.cpu().numpy(), out["done"]) and np.array_equal(env.reward.cpu().numpy(), out["reward"]), t
+        for b in np.nonzero(out["done"])[0]:
+            ora.reset_one(int(b))
+            n_resets += 1
+        want_obs = np.stack([ora.obs_one(b) for b in range(B)])
+        assert np.array_equal(env.obs_view().cpu().numpy(), want_obs), t
+        assert np.array_equal(env.state_rgb.cpu().numpy(), np.stack([ora.state_one(b) for b in range(B)])), t
+        assert np.array_equal(env.grid.cpu().numpy(), ora.grid) and np.array_equal(env.t_buf.cpu().numpy(), ora.envs["t"]), t
+    assert n_resets >= 2 * B
