@@ -246,7 +246,7 @@ def run_reference(a):
 
 
 # --------------------------------------------------------------------------- end-to-end training loop (BASELINE configs[3])
-def train_e2e(a, which=("b200", "b200_batched", "reference")):
+def train_e2e(a, which=("b200", "b200_batched", "b200_batched_4096", "reference")):
     """`run.run_sequential` of the UNCHANGED reference (rollouts + replay + HomophilyLearner updates + test episodes),
     Cleanup default3 / 3 agents / yaml hyper-parameters, t_max env steps: on the CUDA env through the reference's own
     single-env EpisodeRunner ('b200'), through BatchedEpisodeRunner at B=256 with the fused u8 front end, the device epsilon-greedy
@@ -273,16 +273,16 @@ def train_e2e(a, which=("b200", "b200_batched", "reference")):
                   runner_log_interval=1000, learner_log_interval=1000, env_args=dict(num_agents=3, map="default3"))
     for key in which:
         try:
-            if key == "b200_batched":
-                B = 256
-                t_max = 100 * a.train_t_max                                # 10 rollouts of 256 episodes + 10 learner steps
+            if key.startswith("b200_batched"):
+                B = 4096 if key.endswith("4096") else 256
+                t_max = (3 * B * LIMIT) if B == 4096 else 100 * a.train_t_max   # 4 / 10 rollouts of B episodes, one learner step each
                 if cuda:                                                   # untimed: the batched stack's own kernels / cuDNN shapes
                     wcfg = refloop.load_config("cleanup", t_max=1, runner="batched", batch_size_run=B, buffer_size=2 * B,
                                                buffer_cpu_only=False, fused_frontend=True, action_selector="epsilon_greedy_b200",
                                                learner="homophily_learner_b200",
                                                **{**common, "test_nepisode": B, "test_interval": 10 ** 9})
                     refloop.run_training(wcfg, backend="b200")
-                cfg = refloop.load_config("cleanup", t_max=t_max, runner="batched", batch_size_run=B, buffer_size=4 * B,
+                cfg = refloop.load_config("cleanup", t_max=t_max, runner="batched", batch_size_run=B, buffer_size=(4 if B == 256 else 1) * B,
                                           buffer_cpu_only=False, fused_frontend=True, action_selector="epsilon_greedy_b200",
                                           learner="homophily_learner_b200",
                                           **{**common, "test_nepisode": B, "test_interval": t_max})

@@ -141,7 +141,10 @@ class BatchedEpisodeRunner:
         if getattr(self, "front", None) is not None:
             self.front.active = True
         try:
-            return self._run(test_mode)
+            # rollouts never back-propagate; the reference's one-env runner simply lets autograd record them, which at
+            # B envs x 100 steps keeps the whole episode's activations alive (176 GB at B = 4096)
+            with torch.no_grad():
+                return self._run(test_mode)
         finally:
             if getattr(self, "front", None) is not None:
                 self.front.active = False
