@@ -98,7 +98,7 @@ def make_args(cfg: dict):
     args.device = "cuda" if args.use_cuda else "cpu"
     args.unique_token = "refloop"
     if args.use_cuda:
-        torch.cuda.set_device(0)
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))      # one process per GPU under torchrun
     return args
 
 

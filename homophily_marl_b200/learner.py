@@ -116,9 +116,7 @@ class DeviceHomophilyLearner:
             self._dist = dist.is_available() and dist.is_initialized()
         except Exception:
             pass
-        if self._dist:
-            self.bucket.broadcast_params(0)
-            self.target_mac.load_state(self.mac)
+        self._synced = False                                   # rank 0's parameters are broadcast once they live on the device
 
     # ------------------------------------------------------------------ pieces of cal_loss_and_step
     def _unroll(self, mac, batch, detach=False):
@@ -234,7 +232,16 @@ class DeviceHomophilyLearner:
             logs["q_inc_taken_mean"] = torch.gather(q_inc[:, :-1], dim=-1, index=actions_inc).squeeze(-1).mean()
         return loss_env, loss_inc, loss_sim, logs
 
+    def _sync_start(self):
+        """All ranks start from rank 0's parameters (the reference builds the learner on the CPU and moves it afterwards,
+        run.py:132-135, so this cannot happen in __init__ with NCCL)."""
+        if self._dist and not self._synced:
+            self.bucket.broadcast_params(0)
+            self.target_mac.load_state(self.mac)
+        self._synced = True
+
     def cal_loss_and_step(self, batch):
+        self._sync_start()
         loss_env, loss_inc, loss_sim, logs = self.losses(batch)
         self.optimiser_inc.zero_grad()
         self.optimiser_env.zero_grad()
@@ -272,6 +279,7 @@ class DeviceHomophilyLearner:
     def cuda(self):
         self.mac.cuda()
         self.target_mac.cuda()
+        self._sync_start()
 
     def save_models(self, path):
         self.mac.save_models(path)

@@ -98,3 +98,21 @@ def test_flat_bucket_allreduce_and_episode_shards_world2(tmp_path):
         assert torch.all(r[k]["conv_grad"] == r[k]["mean"]) and torch.all(r[k]["env_grad"] == 10 * r[k]["mean"])
         assert torch.all(r[k]["inc_grad"] == 0)                                       # missing gradients count as zeros on every rank
     assert r[0]["shard"] + r[1]["shard"] == list(range(7)) and len(r[0]["shard"]) == 4
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not refloop.available(), reason="reference sources absent (baseline/_ref)")
+def test_data_parallel_learner_on_two_gpus_nccl():
+    """f4 on real hardware: two ranks, one flat-bucket NCCL all-reduce per learner step (profiles/dp_learner_check.py)."""
+    import json
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(_free_port()), os.path.join(ROOT, "profiles", "dp_learner_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["world"] == 2 and res["start_identical"]
+    for s in res["steps"]:
+        assert s["bucket_equals_mean_of_local_grads"] and s["params_identical_after_step"] and s["local_grads_differ_between_ranks"]
