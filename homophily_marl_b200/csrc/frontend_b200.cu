@@ -8,16 +8,17 @@
 //
 // One persistent CTA per SM works on tiles of 128 agent views (GEMM rows):
 //   * warps 0-7  PRODUCERS: conv3x3 + LeakyReLU on the CUDA cores, straight from the u8 planes (27 aligned 32-bit loads give
-//                a 3x3x10 byte patch; 6 output channels x 8 pixels = 1296 FMAs per patch; conv weights come from the
-//                constant bank as FFMA operands).  The activations are the A operand of the FC contraction: each thread
+//                a 3x3x10 byte patch; 6 output channels x 8 pixels = 1296 FMAs per patch, issued as 648 packed fp32-pair
+//                FMAs -- fma.rn.f32x2, SASS FFMA2, new on sm_100 -- with the conv weight as broadcast scalar operand).  The activations are the A operand of the FC contraction: each thread
 //                writes its 8 values of one output channel, split as tf32 hi + lo, into the K-major core-matrix layout the
 //                tensor core reads (no swizzle: 8 rows x 16 B cores, LBO 128 B, SBO 512 B);
 //   * warp 9     TMA: the FC weight tile of the stage ([32 x 16] hi + lo, pre-packed on the host in the same core-matrix
 //                layout) arrives with one cp.async.bulk.tensor.2d (SASS UTMALDG) on the stage's full-barrier;
 //   * warp 8     MMA: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=32, K=8), 16 accumulators in TMEM (512 columns);
 //   * warps 0-3  EPILOGUE after the last stage of a tile: tcgen05.ld (SASS LDTM) -> + bias -> LeakyReLU -> 128-bit stores.
-// A stage is one (pixel row y, 16-pixel block, output channel): A 128 x 16 (hi, lo: 16 KB) + B 32 x 16 (hi, lo: 4 KB); six
-// stages are in flight, so the conv of the next channels overlaps the contraction of the previous ones.
+// A stage is one (pixel row y, 16-pixel block, output channel): A 128 x 16 (hi, lo: 16 KB) + B 32 x 16 (hi, lo: 4 KB).  The
+// activations go through a ring of 6 slots, the weight tiles through their own ring of 16 (the TMA runs two chunks ahead), so
+// the conv of the next channels overlaps the contraction of the previous ones and no stage waits for an L2 round trip.
 //
 // Precision: the reference computes in fp32.  tf32 operands keep 10 mantissa bits, so both operands are split a = hi + lo
 // with hi = rn_tf32(a) and lo = rn_tf32(a - hi) (a - hi is exact in fp32, |lo| <= 2^-11 |a|), and the contraction is
@@ -46,10 +47,13 @@ constexpr int kOC = 6;                       // conv_out   (config/default.yaml:
 constexpr int kFeat = 32;                    // obs_dim_net
 constexpr int kTileM = 128;                  // agent views per tile
 constexpr int kStageK = 16;                  // k' per stage: one output channel x 16 pixels
-constexpr int kStages = 6;
+constexpr int kStages = 6;                               // A ring: activations written by the producers
+constexpr int kBStages = 16;                             // B ring: FC weight tiles fetched by TMA, deep enough to run ~2 chunks ahead
 constexpr int kABytes = kTileM * kStageK * 4;          // 8 KB (one of hi / lo)
 constexpr int kBBytes = kFeat * kStageK * 4;           // 2 KB (one of hi / lo)
-constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes; // 20 KB
+constexpr int kAStageBytes = 2 * kABytes;              // 16 KB
+constexpr int kBStageBytes = 2 * kBBytes;              // 4 KB
+constexpr int kSmemBytes = kStages * kAStageBytes + kBStages * kBStageBytes;   // 160 KB
 constexpr int kProducerThreads = 256;
 constexpr int kThreads = kProducerThreads + 64;        // + MMA warp + TMA warp
 constexpr int kAccs = 16;                                // independent fp32 accumulators in TMEM (see `Precision`)
@@ -123,6 +127,20 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
     return r;
 }
 
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {   // two IEEE fp32 FMAs
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // u8 -> f32 on the full-rate pipes: 0x4B0000bb is the float 8388608 + bb (one PRMT), minus 8388608 (one FADD); I2F is a
 // quarter-rate conversion-pipe instruction and 90 of them per 1296 FFMAs showed up in the profile
 __device__ __forceinline__ float byte_to_float(uint32_t word, int b) {
@@ -134,12 +152,17 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int b) {
 __global__ void __launch_bounds__(kThreads, 1)
 obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ CUtensorMap wmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_tmem_full, bar_tmem_empty;
+    // Two rings with their own barriers: the weight tile of a stage comes from L2 with ~1-2 us of TMA latency, so it must
+    // not wait for the activation slot of the same stage to be released (first version: one ring, 0.6 us per stage even
+    // with the convolution removed).
+    __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_bfull[kBStages], bar_bempty[kBStages],
+                                     bar_tmem_full, bar_tmem_empty;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), kProducerThreads + 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), kProducerThreads / 32); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < kBStages; ++s) { mbar_init(smem_u32(&bar_bfull[s]), 1); mbar_init(smem_u32(&bar_bempty[s]), 1); }
         mbar_init(smem_u32(&bar_tmem_full), 1);
         mbar_init(smem_u32(&bar_tmem_empty), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -178,45 +201,74 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                     for (int dy = 0; dy < 3; ++dy) {
                         const uint8_t* src = view + ch * p.PS + (y + dy) * p.RP + x0;
                         const int k = (ch * 3 + dy) * 3;
+#ifdef FE_DIAG_NOLOAD                                                  // diagnostic build: one load per chunk instead of 27
+                        if (k == 0) nxt[0] = __ldg(reinterpret_cast<const uint32_t*>(src));
+                        nxt[k] = nxt[0] + k; nxt[k + 1] = nxt[0] ^ k; nxt[k + 2] = nxt[0] + 3 * k;
+#else
                         nxt[k] = x0 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
                         nxt[k + 1] = x0 + 4 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src + 4)) : 0u;
                         nxt[k + 2] = x0 + 8 < p.N ? __ldg(reinterpret_cast<const uint32_t*>(src + 8)) : 0u;   // only pixels x0+8, x0+9 < N are used
+#endif
                     }
             };
             request(c_begin);
             for (int c = c_begin; c < c_end; ++c) {
-                // patch[ch][dy][0..9] as floats: raw bytes (the 1/256 lives in the conv weights).  Pixels beyond the image row are
-                // finite garbage (the next row / zeros) that only meets zero FC weights.
-                float patch[3][3][10];
+                uint32_t cur[27];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
+                for (int k = 0; k < 27; ++k) cur[k] = nxt[k];
+                if (c + 1 < c_end) request(c + 1);
+                // The conv runs on packed fp32 pairs (fma.rn.f32x2 -> SASS FFMA2, new on sm_100): one instruction updates the
+                // accumulators of two neighbouring output pixels with the same (broadcast) weight.  acc2[oc][j] = pixels 2j, 2j+1.
+                // A pixel row is kept as aligned pairs E2 (taps dx = 0, 2) and as pairs shifted by one pixel O2 (tap dx = 1).
+                // One input plane at a time, so that only 3 rows of the patch are live next to the 48 accumulators.  Raw bytes go
+                // in (the 1/256 lives in the conv weights); pixels beyond the image row are finite garbage that only meets
+                // zero FC weights.
+                unsigned long long acc2[kOC][4];
+#pragma unroll
+                for (int oc = 0; oc < kOC; ++oc) {
+                    const unsigned long long b2 = pack2(p.conv_b[oc], p.conv_b[oc]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc2[oc][j] = b2;
+                }
+#ifdef FE_DIAG_NOCONV
+#pragma unroll
+                for (int k = 0; k < 27; ++k) acc2[k % kOC][k & 3] ^= cur[k];
+#else
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    unsigned long long E2[3][5], O2[3][4];
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         const int k = (ch * 3 + dy) * 3;
+                        float e[10];
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            patch[ch][dy][b] = byte_to_float(nxt[k], b);
-                            patch[ch][dy][4 + b] = byte_to_float(nxt[k + 1], b);
-                        }
-                        patch[ch][dy][8] = byte_to_float(nxt[k + 2], 0);
-                        patch[ch][dy][9] = byte_to_float(nxt[k + 2], 1);
+                        for (int b = 0; b < 4; ++b) { e[b] = byte_to_float(cur[k], b); e[4 + b] = byte_to_float(cur[k + 1], b); }
+                        e[8] = byte_to_float(cur[k + 2], 0);
+                        e[9] = byte_to_float(cur[k + 2], 1);
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) E2[dy][j] = pack2(e[2 * j], e[2 * j + 1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) O2[dy][j] = pack2(e[2 * j + 1], e[2 * j + 2]);
                     }
-                if (c + 1 < c_end) request(c + 1);
 #pragma unroll
-                for (int oc = 0; oc < kOC; ++oc, ++it) {
-                    float acc[8];
-#pragma unroll
-                    for (int px = 0; px < 8; ++px) acc[px] = p.conv_b[oc];
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
+                    for (int oc = 0; oc < kOC; ++oc)
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
                                 const float w = p.conv_w[oc * 27 + ch * 9 + dy * 3 + dx];
+                                const unsigned long long w2 = pack2(w, w);
 #pragma unroll
-                                for (int px = 0; px < 8; ++px) acc[px] = fmaf(w, patch[ch][dy][px + dx], acc[px]);
+                                for (int j = 0; j < 4; ++j)
+                                    acc2[oc][j] = fma2(w2, dx == 0 ? E2[dy][j] : (dx == 1 ? O2[dy][j] : E2[dy][j + 1]), acc2[oc][j]);
                             }
+                }
+#endif
+#pragma unroll
+                for (int oc = 0; oc < kOC; ++oc, ++it) {
+                    float acc[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) unpack2(acc2[oc][j], acc[2 * j], acc[2 * j + 1]);
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int px = 0; px < 8; ++px) {                           // (padding pixels meet zero weights: no masking)
@@ -226,14 +278,17 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                     }
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);               // the MMAs that read this slot have completed
-                    uint8_t* a_hi = smem + s * kStageBytes + (r >> 3) * 512 + (r & 7) * 16 + strip * 256;
+                    uint8_t* a_hi = smem + s * kAStageBytes + (r >> 3) * 512 + (r & 7) * 16 + strip * 256;
                     uint8_t* a_lo = a_hi + kABytes;
                     *reinterpret_cast<uint4*>(a_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(a_hi + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     *reinterpret_cast<uint4*>(a_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     *reinterpret_cast<uint4*>(a_lo + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+#ifndef FE_DIAG_NOFENCE
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> tensor-core reads
-                    mbar_arrive(smem_u32(&bar_full[s]));
+#endif
+                    __syncwarp();                                               // every lane's writes + fence precede the warp's one arrival
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
                 }
             }
             if (warp < 4) {
@@ -293,11 +348,13 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
             uint32_t used = 0;                                                 // accumulators already written in this item
             for (int st = 0; st < stages_here; ++st, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-                mbar_wait_relaxed(smem_u32(&bar_full[s]), ph);                 // A written by 256 producers, B landed by TMA
+                const uint32_t sb = it % kBStages, phb = (it / kBStages) & 1u;
+                mbar_wait(smem_u32(&bar_bfull[sb]), phb);                      // weight tile landed (TMA, issued well ahead)
+                mbar_wait(smem_u32(&bar_full[s]), ph);                         // activations written by the 256 producers
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t a_hi = smem_base + s * kStageBytes, a_lo = a_hi + kABytes;
-                    const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + kBBytes;
+                    const uint32_t a_hi = smem_base + s * kAStageBytes, a_lo = a_hi + kABytes;
+                    const uint32_t b_hi = smem_base + kStages * kAStageBytes + sb * kBStageBytes, b_lo = b_hi + kBBytes;
 #pragma unroll
                     for (int ks = 0; ks < kStageK / 8; ++ks) {                 // one K=8 step = two 16-byte cores, 256 B further on
                         const uint64_t dah = umma_desc(a_hi + ks * 256, 128, 512), dal = umma_desc(a_lo + ks * 256, 128, 512);
@@ -311,7 +368,8 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                         umma_tf32(tmem_base, dah, dbl, idesc, 1u);
                         used |= 1u | (1u << acc);
                     }
-                    umma_commit(smem_u32(&bar_empty[s]));                      // frees the slot when these MMAs have read it
+                    umma_commit(smem_u32(&bar_empty[s]));                      // frees both slots when these MMAs have read them
+                    umma_commit(smem_u32(&bar_bempty[sb]));
                     if (st == stages_here - 1) umma_commit(smem_u32(&bar_tmem_full));
                 }
                 __syncwarp();
@@ -325,11 +383,11 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                 const int part = item % p.split;
                 const int st_begin = (part * p.n_chunks / p.split) * kOC, st_end = ((part + 1) * p.n_chunks / p.split) * kOC;
                 for (int st = st_begin; st < st_end; ++st, ++it) {
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-                    mbar_wait_relaxed(smem_u32(&bar_empty[s]), ph ^ 1u);
-                    const uint32_t full = smem_u32(&bar_full[s]);
-                    mbar_arrive_expect_tx(full, 2 * kBBytes);
-                    tma_load_2d(smem_base + s * kStageBytes + 2 * kABytes, &wmap, full, 0, st * 4);   // 4 rows of 256 floats = hi + lo
+                    const uint32_t sb = it % kBStages, phb = (it / kBStages) & 1u;
+                    mbar_wait_relaxed(smem_u32(&bar_bempty[sb]), phb ^ 1u);
+                    const uint32_t full = smem_u32(&bar_bfull[sb]);
+                    mbar_arrive_expect_tx(full, kBStageBytes);
+                    tma_load_2d(smem_base + kStages * kAStageBytes + sb * kBStageBytes, &wmap, full, 0, st * 4);   // 4 rows of 256 floats = hi + lo
                 }
             }
         }
@@ -439,7 +497,7 @@ int ssd_frontend_create(int32_t view, const float* conv_w, const float* conv_b, 
             if (cr != CUDA_SUCCESS) { g_front_cuda_error = (int)cr; rc = SSD_ERR_CUDA; }
         }
     }
-    f->smem_bytes = (size_t)kStages * kStageBytes + 1024;
+    f->smem_bytes = (size_t)kSmemBytes + 1024;
     if (e == cudaSuccess && rc == SSD_OK)
         e = cudaFuncSetAttribute(obs_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_bytes);
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
