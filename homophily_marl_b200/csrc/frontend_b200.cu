@@ -364,8 +364,10 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                         // accumulators, the (2^-11 smaller) lo terms have their own; the epilogue adds the 16 partial sums
                         const uint32_t acc = 1u + (uint32_t)(st * (kStageK / 8) + ks) % (kAccs - 1);
                         umma_tf32(tmem_base + acc * kFeat, dah, dbh, idesc, (used >> acc) & 1u);
+#ifndef FE_DIAG_HIONLY                                                  // diagnostic build: one MMA per K step instead of three
                         umma_tf32(tmem_base, dal, dbh, idesc, used & 1u);
                         umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+#endif
                         used |= 1u | (1u << acc);
                     }
                     umma_commit(smem_u32(&bar_empty[s]));                      // frees both slots when these MMAs have read them
