@@ -215,6 +215,15 @@ struct SubWarp {
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 
+// lanes j < n whose value equals this lane's: what __match_any_sync returns for the agent lanes, from n pipelined shuffles
+// (MATCH.ANY costs 3-4 % of a Cleanup step per use, profiles/r2_notes.md)
+template <class SW>
+__device__ __forceinline__ unsigned equal_lanes(const SW& w, int v, int n) {
+    unsigned m = 0;
+    for (int j = 0; j < n; ++j) m |= (unsigned)(w.shfl(v, j) == v) << j;
+    return m;
+}
+
 // sub-warp-strided loop with the first trip peeled (trip counts here are almost always 0 or 1)
 template <int STRIDE, typename F>
 __device__ __forceinline__ void warp_for(int n, int lane, F f) {
@@ -264,7 +273,7 @@ __device__ __forceinline__ void update_moves(const SW& w, const GEO& g, const KP
     int mv = prop;                                            // live agent_moves[i]
 
     // ---- phase 1: contested cells in lexicographic order of the ORIGINAL proposals (543-609)
-    const unsigned grp = w.match(mover ? prop : -1000 - lane);
+    const unsigned grp = equal_lanes(w, mover ? prop : -1000 - lane, p.n);
     unsigned pending = w.ballot(mover && __popc(grp) >= 2);
     if (pending) {
         uint32_t prio = 0;
@@ -294,6 +303,16 @@ __device__ __forceinline__ void update_moves(const SW& w, const GEO& g, const KP
         }
     }
     // ---- phase 2: iterate until every move is made or dropped (612-661)
+    // Fast path: if no mover's target is occupied by ANOTHER agent, the sequential walk below moves every mover (targets are
+    // unique after phase 1 or the mover's own cell, and nobody enters a cell that is somebody's target), so all move at once.
+    {
+        bool blocked = false;
+        for (int j = 0; j < p.n; ++j) blocked |= (w.shfl(pos, j) == mv) && (j != lane);
+        if (w.ballot(((in_moves >> lane) & 1u) && blocked) == 0) {
+            if ((in_moves >> lane) & 1u) pos = mv;
+            return;
+        }
+    }
     while (in_moves) {
         const int spos = pos;                                  // snapshot dict of this pass (613)
         const unsigned snap = in_moves;
@@ -758,9 +777,8 @@ __device__ __forceinline__ void gather_direct(const SW& w, const GEO& g, const K
 
 template <class SW, class GEO>
 __device__ __forceinline__ void render(const SW& w, const GEO& g, const KParams& p, const uint8_t* sg, uint8_t* pmap, const uint32_t* lut_s,
-                                       int lane, bool is_agent, int pos, int ori, int env) {
-    const unsigned same = w.match(pos);
-    const bool top = is_agent && lane == 31 - __clz(same);   // later index overwrites (map_env.py:370)
+                                       int lane, bool is_agent, int pos, int ori, int env, unsigned same) {
+    const bool top = is_agent && lane == 31 - __clz(same);   // later index overwrites (map_env.py:370); same = lanes on this lane's cell
     int r0 = 0, c0 = 0;
     if (is_agent) { r0 = g.divW(pos); c0 = pos - r0 * g.W(); }
 
@@ -893,11 +911,15 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
         w.sync();
 
         int apples = (int)(cnt & 0xffffu), waste = (int)(cnt >> 16);
+        // lanes standing on this lane's cell: MATCH.ANY is slow (3-4 % of the step each in the profile), positions do not change
+        // after update_moves, so it is evaluated once and shared by consume, the occupancy strip and the render
+        unsigned same = 1u << lane;                            // reset: distinct spawn points
+        if (MODE == MODE_RENDER) same = equal_lanes(w, pos, p.n);
         if (MODE == MODE_STEP) {
             int reward = 0, clean_num = 0;
             update_moves(w, g, p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
             // consume in index order: the lowest index on a cell eats the apple (253-256); mark occupancy
-            const unsigned same = w.match(pos);
+            same = equal_lanes(w, pos, p.n);
             const int here = is_agent ? sg[pos] : 0;
             const bool first = is_agent && lane == __ffs(same) - 1;
             const unsigned ate = w.ballot(first && here == SSD_CELL_APPLE);
@@ -954,7 +976,6 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
         }
 
         if (MODE != MODE_RENDER) {                                 // strip the occupancy bits, write the state back
-            const unsigned same = w.match(pos);
             if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
             w.sync();
             uint4* dst = reinterpret_cast<uint4*>(p.grid + (size_t)env * g.GS());
@@ -971,7 +992,7 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
             w.sync();                                          // the write-back above has read the staged grid
             if (is_agent) sg[pos] = 7;
             w.sync();
-            render(w, g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env);
+            render(w, g, p, sg, pmap, lut_s, lane, is_agent, pos, ori, env, same);
         }
     }
 }
