@@ -858,12 +858,11 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
     using SW = SubWarp<LPE>;
     const GEO g(p);
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t lut_s[16];
-    if (threadIdx.x < 16) lut_s[threadIdx.x] = p.lut[threadIdx.x];
-    __syncthreads();
+    __shared__ uint32_t lut_all[kWarps * 2][16];              // colour LUT, one private copy per (sub-)warp: no CTA barrier anywhere
     const int warp = threadIdx.x >> 5;
     const SW w(threadIdx.x & 31);
     const int lane = w.lane;                                  // lane within the sub-warp that owns an env
+    uint32_t* lut_s = lut_all[warp * SW::kEnvs + w.sub];
     // per-env tile: [front slack][grid GS][back slack][nibble maps (map path only)]
     uint8_t* tile = smem + ((size_t)warp * SW::kEnvs + w.sub) * (g.padF() + g.GS() + g.padB() + g.PMS());
     uint8_t* sg = tile + g.padF();
@@ -895,7 +894,8 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
                                                   : reinterpret_cast<const uint4*>(p.grid + (size_t)env * g.GS());
             uint4 g0 = make_uint4(0, 0, 0, 0);
             if (lane < n16) g0 = src[lane];
-            if (p.obs) {                                      // while the state loads are in flight
+            if (lane < 16) lut_s[lane] = p.lut[lane];         // while the state loads are in flight (made visible by w.sync below)
+            if (p.obs) {
                 if (g.direct()) {                             // zero the slack around the grid (read, then masked, by the gather)
                     for (int i = lane; i < (g.padF() >> 4); i += SW::kLanes) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
                     for (int i = lane; i < (g.padB() >> 4); i += SW::kLanes) reinterpret_cast<uint4*>(sg + g.GS())[i] = make_uint4(0, 0, 0, 0);
