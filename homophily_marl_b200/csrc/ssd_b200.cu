@@ -212,6 +212,7 @@ struct SubWarp {
     template <typename T> __device__ __forceinline__ T rmin(T v) const { return __reduce_min_sync(mask, v); }
     template <typename T> __device__ __forceinline__ T rmax(T v) const { return __reduce_max_sync(mask, v); }
     template <typename T> __device__ __forceinline__ T radd(T v) const { return __reduce_add_sync(mask, v); }
+    __device__ __forceinline__ unsigned ror(unsigned v) const { return __reduce_or_sync(mask, v); }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 
@@ -222,6 +223,17 @@ __device__ __forceinline__ unsigned equal_lanes(const SW& w, int v, int n) {
     unsigned m = 0;
     for (int j = 0; j < n; ++j) m |= (unsigned)(w.shfl(v, j) == v) << j;
     return m;
+}
+// Cheap sufficient test for "the values of the lanes in `who` are pairwise distinct": two 32-bucket bit filters, OR-reduced over
+// the warp (REDUX.OR); if either filter shows one bit per participating lane there is no duplicate.  False alarms (hash
+// collisions) only send the caller to the exact shuffle loop.
+template <class SW>
+__device__ __forceinline__ bool surely_distinct(const SW& w, int v, bool in, unsigned who) {
+    const int cnt = __popc(who);
+    const unsigned f0 = w.ror(in ? 1u << (v & 31) : 0u);
+    if (__popc(f0) == cnt) return true;
+    const unsigned f1 = w.ror(in ? 1u << ((v >> 5) & 31) : 0u);
+    return __popc(f1) == cnt;
 }
 
 // sub-warp-strided loop with the first trip peeled (trip counts here are almost always 0 or 1)
@@ -273,8 +285,11 @@ __device__ __forceinline__ void update_moves(const SW& w, const GEO& g, const KP
     int mv = prop;                                            // live agent_moves[i]
 
     // ---- phase 1: contested cells in lexicographic order of the ORIGINAL proposals (543-609)
-    const unsigned grp = equal_lanes(w, mover ? prop : -1000 - lane, p.n);
-    unsigned pending = w.ballot(mover && __popc(grp) >= 2);
+    unsigned pending = 0;                                     // movers whose proposal is shared with another mover
+    if (!surely_distinct(w, prop, mover, in_moves)) {
+        const unsigned grp = equal_lanes(w, mover ? prop : -1000 - lane, p.n);
+        pending = w.ballot(mover && __popc(grp) >= 2);
+    }
     if (pending) {
         uint32_t prio = 0;
         if (mover) prio = p.d_prio ? p.d_prio[(size_t)env * p.n + lane] : philox_word(p, gid, tick, 0, (uint32_t)lane);
@@ -305,11 +320,19 @@ __device__ __forceinline__ void update_moves(const SW& w, const GEO& g, const KP
     // ---- phase 2: iterate until every move is made or dropped (612-661)
     // Fast path: if no mover's target is occupied by ANOTHER agent, the sequential walk below moves every mover (targets are
     // unique after phase 1 or the mover's own cell, and nobody enters a cell that is somebody's target), so all move at once.
+    // (A mover whose target is its own cell never changes anything, whoever else stands there.)  The occupancy test is first
+    // made against a 32-bucket bit filter of all agents' cells; only a possible hit pays for the exact shuffle loop.
     {
-        bool blocked = false;
-        for (int j = 0; j < p.n; ++j) blocked |= (w.shfl(pos, j) == mv) && (j != lane);
-        if (w.ballot(((in_moves >> lane) & 1u) && blocked) == 0) {
-            if ((in_moves >> lane) & 1u) pos = mv;
+        const bool mine = (in_moves >> lane) & 1u;
+        const unsigned cells = w.ror(is_agent ? 1u << (pos & 31) : 0u);
+        bool blocked = mine && mv != pos && ((cells >> (mv & 31)) & 1u);
+        if (w.ballot(blocked)) {
+            blocked = false;
+            for (int j = 0; j < p.n; ++j) blocked |= (w.shfl(pos, j) == mv) && (j != lane);
+            blocked = blocked && mine && mv != pos;
+        }
+        if (w.ballot(blocked) == 0) {
+            if (mine) pos = mv;
             return;
         }
     }
@@ -919,7 +942,7 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
             int reward = 0, clean_num = 0;
             update_moves(w, g, p, sg, lane, is_agent, act, pos, ori, env, gid, tick);                 // map_env.py:251
             // consume in index order: the lowest index on a cell eats the apple (253-256); mark occupancy
-            same = equal_lanes(w, pos, p.n);
+            same = surely_distinct(w, pos, is_agent, w.ballot(is_agent)) ? (1u << lane) : equal_lanes(w, pos, p.n);
             const int here = is_agent ? sg[pos] : 0;
             const bool first = is_agent && lane == __ffs(same) - 1;
             const unsigned ate = w.ballot(first && here == SSD_CELL_APPLE);
