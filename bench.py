@@ -260,17 +260,15 @@ def train_e2e(a, which=("b200", "b200_batched", "b200_batched_4096", "reference"
         return out
     import torch
     cuda = torch.cuda.is_available()
-    # untimed warm-up of everything the three timed runs share (CUDA context, cuDNN/cuBLAS handles, autograd kernels):
-    # one episode + enough learner updates to touch every kernel, on the first backend that will be timed
+    common = dict(seed=a.seed, use_cuda=cuda, save_model=False, test_nepisode=4, test_interval=1000, log_interval=1000,
+                  runner_log_interval=1000, learner_log_interval=1000, env_args=dict(num_agents=3, map="default3"))
+    # untimed warm-up with the SAME shapes as the timed single-env runs (CUDA context, cuDNN / cuBLAS heuristics for batch 1
+    # rollouts and batch 16 learner steps, autograd kernels): 18 episodes, two learner updates
     try:
-        warm = refloop.load_config("cleanup", seed=a.seed, use_cuda=cuda, save_model=False, t_max=450, batch_size=2, buffer_size=8,
-                                   test_nepisode=1, test_interval=10 ** 9, log_interval=10 ** 9, runner_log_interval=10 ** 9,
-                                   learner_log_interval=10 ** 9, env_args=dict(num_agents=3, map="default3"))
+        warm = refloop.load_config("cleanup", t_max=min(1700, a.train_t_max), **common)
         refloop.run_training(warm, backend="reference" if (which == ("reference",) or not cuda) else "b200")
     except Exception as e:
         out["warmup_error"] = f"{type(e).__name__}: {e}"[:200]
-    common = dict(seed=a.seed, use_cuda=cuda, save_model=False, test_nepisode=4, test_interval=1000, log_interval=1000,
-                  runner_log_interval=1000, learner_log_interval=1000, env_args=dict(num_agents=3, map="default3"))
     for key in which:
         try:
             if key.startswith("b200_batched"):
