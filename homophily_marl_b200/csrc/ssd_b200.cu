@@ -2,15 +2,16 @@
 //
 // Design: one warp owns one env instance for a whole step.
 //   * lanes 0..n-1 ARE the agents during move/rotate, conflict resolution, consume and beams:
-//     collisions, swaps, chains and cycles are resolved with __ballot/__match/__shfl/redux,
-//     keeping the reference's sequential phase structure (map_env.py:477-661);
+//     collisions, swaps, chains and cycles are resolved with __ballot/__shfl/redux (bit-filter pre-tests
+//     with REDUX.OR, exact shuffle loops only on a possible hit), keeping the reference's sequential
+//     phase structure (map_env.py:477-661);
 //   * lanes are spawn candidates during apple/waste spawning (4 apple points or 2 waste
 //     points per Philox4x32-10 call);
-//   * lanes are output pixel ROWS during the egocentric render: a row of the rotated window is one
-//     run of N nibbles in a zero-padded nibble-packed index map (or its transpose) held in shared memory,
-//     so a lane funnel-shifts it to pixel 0, colours 4 pixels per PRMT through an 8-entry register LUT
-//     and writes the finished row with one 256-bit (st.global.v8.b32, SASS STG.E.ENL2.256) or 128-bit
-//     store per plane.
+//   * lanes are output pixel ROWS during the egocentric render.  Small views (N <= 16, Cleanup) are
+//     gathered straight from the staged byte grid; large views (Harvest, N = 31) read one run of N
+//     nibbles from a zero-padded nibble-packed index map (or its transpose) held in shared memory.
+//     Either way a lane colours 4 pixels per PRMT through an 8-entry register LUT and writes the
+//     finished row with one 256-bit (st.global.v8.b32, SASS STG.E.ENL2.256) or 128-bit store per plane.
 // The env's grid is staged in shared memory for the whole step.  No tensor cores: nothing here is a
 // contraction.  HBM traffic per env-step is the algorithmic 2G + n(3N^2+11)+3 bytes (+ row padding),
 // ~98% of it observation WRITES.
