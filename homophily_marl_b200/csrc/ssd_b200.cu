@@ -437,8 +437,11 @@ __device__ __forceinline__ void spawn(const SW& w, const GEO& g, const KParams& 
         tA = __ldg(&m->thr_apple[waste]);
         tW = __ldg(&m->thr_waste[waste]);
     }
-    // apples: 4 candidate points per lane per Philox call; decisions use the pre-spawn grid
+    // apples: 4 candidate points per lane per Philox call; decisions use the pre-spawn grid.  In Cleanup a decision reads
+    // only its own cell (and apple points and waste points are different cells), so the apple is written at once; Harvest's
+    // 3x3 neighbour count needs every decision to see the pre-spawn grid, so its apples are applied in a second pass.
     unsigned long long decided = 0;
+    int n_new = 0;
     if (tA != 0) {
         int it = 0;
         for (int j = lane; j < p.n_apple4; j += SW::kLanes, ++it) {
@@ -464,7 +467,10 @@ __device__ __forceinline__ void spawn(const SW& w, const GEO& g, const KParams& 
                     thr = p.thr_harvest[cnt < 3 ? cnt : 3];
                 }
                 const uint32_t u = p.d_uapple ? p.d_uapple[(size_t)env * g.G() + c] : pick(r, q);
-                if (u < thr) decided |= 1ull << (it * 4 + q);
+                if (u < thr) {
+                    if (g.kind() == SSD_KIND_CLEANUP) { sg[c] = SSD_CELL_APPLE; ++n_new; }
+                    else decided |= 1ull << (it * 4 + q);
+                }
             }
         }
     }
@@ -492,7 +498,7 @@ __device__ __forceinline__ void spawn(const SW& w, const GEO& g, const KParams& 
         }
     }
     w.sync();                                             // every decision read the pre-spawn grid
-    if (decided) {
+    if (g.kind() == SSD_KIND_HARVEST && decided) {
         int it = 0;
         for (int j = lane; j < p.n_apple4; j += SW::kLanes, ++it) {
             const ushort4 pts = __ldg(reinterpret_cast<const ushort4*>(m->apple_pts) + j);
@@ -503,7 +509,8 @@ __device__ __forceinline__ void spawn(const SW& w, const GEO& g, const KParams& 
     }
     if (wcell >= 0 && lane == 0) sg[wcell] = (uint8_t)(SSD_CELL_WASTE | (sg[wcell] & kOcc));
     w.sync();
-    if (w.ballot(decided != 0)) apples += w.radd(__popcll(decided));
+    if (g.kind() == SSD_KIND_HARVEST) n_new = __popcll(decided);
+    if (w.ballot(n_new != 0)) apples += w.radd(n_new);
     waste += wcell >= 0;
 }
 
