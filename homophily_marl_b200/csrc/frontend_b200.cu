@@ -46,21 +46,36 @@ namespace {
 constexpr int kOC = 6;                       // conv_out   (config/default.yaml: conv_out 6, conv_kernel 3, conv_stride 1)
 constexpr int kFeat = 32;                    // obs_dim_net
 constexpr int kTileM = 128;                  // agent views per tile
-constexpr int kStageK = 16;                  // k' per stage: one output channel x 16 pixels
-constexpr int kStages = 6;                               // A ring: activations written by the producers
-constexpr int kBStages = 16;                             // B ring: FC weight tiles fetched by TMA, deep enough to run ~2 chunks ahead
-constexpr int kABytes = kTileM * kStageK * 4;          // 8 KB (one of hi / lo)
-constexpr int kBBytes = kFeat * kStageK * 4;           // 2 KB (one of hi / lo)
-constexpr int kAStageBytes = 2 * kABytes;              // 16 KB
-constexpr int kBStageBytes = 2 * kBBytes;              // 4 KB
-constexpr int kSmemBytes = kStages * kAStageBytes + kBStages * kBStageBytes;   // 160 KB
+#ifndef FE_OC_PER_STAGE
+#define FE_OC_PER_STAGE 3
+#endif
+#ifndef FE_STAGES
+#define FE_STAGES 2
+#endif
+#ifndef FE_BSTAGES
+#define FE_BSTAGES 4
+#endif
+constexpr int kG = FE_OC_PER_STAGE;          // output channels per pipeline stage (1, 2, 3 or 6)
+constexpr int kStageK = 16 * kG;             // k' per stage: kG output channels x 16 pixels
+constexpr int kStagesPerChunk = kOC / kG;
+constexpr int kStages = FE_STAGES;                       // A ring: activations written by the producers
+constexpr int kBStages = FE_BSTAGES;                     // B ring: FC weight tiles fetched by TMA, deep enough to run ~2 chunks ahead
+constexpr int kABytes = kTileM * kStageK * 4;          // 8 KB x kG (one of hi / lo)
+constexpr int kBBytes = kFeat * kStageK * 4;           // 2 KB x kG (one of hi / lo)
+constexpr int kASbo = 512 * kG, kBSbo = 512 * kG;      // bytes between 8-row groups: 4 kG cores of 128 B
+constexpr int kAStageBytes = 2 * kABytes;
+constexpr int kBStageBytes = 2 * kBBytes;
+constexpr int kSmemBytes = kStages * kAStageBytes + kBStages * kBStageBytes;
+static_assert(kOC % kG == 0, "stage must hold whole output channels");
+static_assert(kSmemBytes + 1024 <= 227 * 1024, "rings exceed shared memory");
 constexpr int kProducerThreads = 256;
 constexpr int kThreads = kProducerThreads + 64;        // + MMA warp + TMA warp
 constexpr int kAccs = 16;                                // independent fp32 accumulators in TMEM (see `Precision`)
 constexpr uint32_t kTmemCols = kAccs * kFeat;          // 512 columns: the whole TMEM of the SM (one CTA per SM)
 
 struct FrontParams {
-    float conv_w[kOC * 27];                  // [oc][ch][dy][dx], pre-scaled by 1/256 (exact): the conv sees raw bytes
+    unsigned long long conv_w2[kOC / 2][27]; // [oc pair][ch][dy][dx] = (w[2 op], w[2 op + 1]) as packed fp32, pre-scaled by 1/256
+                                             // (exact): the conv sees raw bytes
     float conv_b[kOC];
     float fc_b[kFeat];
     float slope;
@@ -182,61 +197,73 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
         // ------------------------------------------------------------------ producers (+ epilogue on warps 0-3)
         const int r = tid & 127, strip = tid >> 7;             // GEMM row within the tile; 8-pixel half of the 16-pixel block
         uint32_t it = 0, item_n = 0;
+        unsigned long long bias2[kOC / 2];
+#pragma unroll
+        for (int op = 0; op < kOC / 2; ++op) bias2[op] = pack2(p.conv_b[2 * op], p.conv_b[2 * op + 1]);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
             const int tile = item / p.split, part = item - tile * p.split;
             const int c_begin = part * p.n_chunks / p.split, c_end = (part + 1) * p.n_chunks / p.split;
-            const int stages_here = (c_end - c_begin) * kOC;
+            const int stages_here = (c_end - c_begin) * kStagesPerChunk;
             const long long row = (long long)tile * kTileM + r;
-            // The 27 words of the NEXT chunk's patch are requested before the current chunk is convolved, so their L2 latency is
-            // hidden behind 1 296 FFMAs.  (A shared-memory row window filled with coalesced loads was measured and dropped: the
-            // per-row CTA barrier cost more than the sectors it saved -- V=15: 515 us instead of 397 us, profiles/r2_notes.md.)
+            // Chunks run down a 16-pixel column (c = xb * P + y), so consecutive chunks share two of their three patch rows: the
+            // thread keeps a 3-row window of raw words (3 planes x 3 words per row) and loads ONE new row per chunk -- requested
+            // before the current chunk is convolved, so its L2 latency hides behind the FMAs.  (A shared-memory row window filled
+            // with coalesced loads was measured and dropped: the per-row CTA barrier cost more than the sectors it saved --
+            // V=15: 515 us instead of 397 us, profiles/r2_notes.md.)
             const long long row_ld = row < p.rows ? row : p.rows - 1;          // partial last tile: compute on a valid row, never store
             const uint8_t* view = p.obs + row_ld * p.AS;
-            uint32_t nxt[27];
-            auto request = [&](int c) {
-                const int y = c / p.XB, xb = c - y * p.XB, x0 = xb * 16 + strip * 8;
+            uint32_t win[3][9], nxt[9];
+            auto load_row = [&](uint32_t (&dst)[9], int yy, int xb) {
+                const int x0 = xb * 16 + strip * 8;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const uint8_t* src = view + ch * p.PS + yy * p.RP + x0;
+#ifdef FE_DIAG_NOLOAD                                                  // diagnostic build: one load per row instead of 9
+                    if (ch == 0) dst[0] = __ldg(reinterpret_cast<const uint32_t*>(src));
+                    dst[ch * 3] = dst[0] + ch; dst[ch * 3 + 1] = dst[0] ^ ch; dst[ch * 3 + 2] = dst[0] + 3 * ch;
+#else
+                    dst[ch * 3] = x0 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
+                    dst[ch * 3 + 1] = x0 + 4 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src + 4)) : 0u;
+                    dst[ch * 3 + 2] = x0 + 8 < p.N ? __ldg(reinterpret_cast<const uint32_t*>(src + 8)) : 0u;   // only pixels x0+8, x0+9 < N are used
+#endif
+                }
+            };
+            for (int c = c_begin; c < c_end; ++c) {
+                const int xb = c / p.P, y = c - xb * p.P;
+                if (c == c_begin || y == 0) {                                  // first chunk of the item or of a column: whole window
+                    load_row(win[0], y, xb);
+                    load_row(win[1], y + 1, xb);
+                    load_row(nxt, y + 2, xb);
+                }
+#pragma unroll
+                for (int k = 0; k < 9; ++k) win[2][k] = nxt[k];
+                if (c + 1 < c_end && y + 1 < p.P) load_row(nxt, y + 3, xb);    // the row the next chunk adds
+                uint32_t cur[27];
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const uint8_t* src = view + ch * p.PS + (y + dy) * p.RP + x0;
-                        const int k = (ch * 3 + dy) * 3;
-#ifdef FE_DIAG_NOLOAD                                                  // diagnostic build: one load per chunk instead of 27
-                        if (k == 0) nxt[0] = __ldg(reinterpret_cast<const uint32_t*>(src));
-                        nxt[k] = nxt[0] + k; nxt[k + 1] = nxt[0] ^ k; nxt[k + 2] = nxt[0] + 3 * k;
-#else
-                        nxt[k] = x0 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
-                        nxt[k + 1] = x0 + 4 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src + 4)) : 0u;
-                        nxt[k + 2] = x0 + 8 < p.N ? __ldg(reinterpret_cast<const uint32_t*>(src + 8)) : 0u;   // only pixels x0+8, x0+9 < N are used
-#endif
-                    }
-            };
-            request(c_begin);
-            for (int c = c_begin; c < c_end; ++c) {
-                uint32_t cur[27];
+                    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int k = 0; k < 27; ++k) cur[k] = nxt[k];
-                if (c + 1 < c_end) request(c + 1);
-                // The conv runs on packed fp32 pairs (fma.rn.f32x2 -> SASS FFMA2, new on sm_100): one instruction updates the
-                // accumulators of two neighbouring output pixels with the same (broadcast) weight.  acc2[oc][j] = pixels 2j, 2j+1.
-                // A pixel row is kept as aligned pairs E2 (taps dx = 0, 2) and as pairs shifted by one pixel O2 (tap dx = 1).
-                // One input plane at a time, so that only 3 rows of the patch are live next to the 48 accumulators.  Raw bytes go
-                // in (the 1/256 lives in the conv weights); pixels beyond the image row are finite garbage that only meets
-                // zero FC weights.
-                unsigned long long acc2[kOC][4];
+                        for (int w = 0; w < 3; ++w) cur[(ch * 3 + dy) * 3 + w] = win[dy][ch * 3 + w];
 #pragma unroll
-                for (int oc = 0; oc < kOC; ++oc) {
-                    const unsigned long long b2 = pack2(p.conv_b[oc], p.conv_b[oc]);
+                for (int k = 0; k < 9; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; }
+                // The conv runs on packed fp32 pairs (fma.rn.f32x2 -> SASS FFMA2, new on sm_100): one instruction updates the same
+                // output pixel of TWO output channels -- the input pixel is the broadcast scalar operand (R.F32), the two conv
+                // weights a packed uniform-register pair (UR.F32x2) read straight from the kernel parameters, so no register
+                // pairs have to be assembled (pairing neighbouring pixels instead cost 380 MOVs per 648 FFMA2).
+                // acc2[op][px] = channels (2 op, 2 op + 1) of pixel px.  Raw bytes go in (the 1/256 lives in the conv weights);
+                // pixels beyond the image row are finite garbage that only meets zero FC weights.
+                unsigned long long acc2[kOC / 2][8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc2[oc][j] = b2;
-                }
+                for (int op = 0; op < kOC / 2; ++op)
+#pragma unroll
+                    for (int px = 0; px < 8; ++px) acc2[op][px] = bias2[op];
 #ifdef FE_DIAG_NOCONV
 #pragma unroll
-                for (int k = 0; k < 27; ++k) acc2[k % kOC][k & 3] ^= cur[k];
+                for (int k = 0; k < 27; ++k) acc2[k % 3][k & 7] ^= cur[k];
 #else
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    unsigned long long E2[3][5], O2[3][4];
+                for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         const int k = (ch * 3 + dy) * 3;
@@ -246,44 +273,46 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                         e[8] = byte_to_float(cur[k + 2], 0);
                         e[9] = byte_to_float(cur[k + 2], 1);
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) E2[dy][j] = pack2(e[2 * j], e[2 * j + 1]);
+                        for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) O2[dy][j] = pack2(e[2 * j + 1], e[2 * j + 2]);
-                    }
+                            for (int op = 0; op < kOC / 2; ++op) {
+                                const unsigned long long w2 = p.conv_w2[op][ch * 9 + dy * 3 + dx];
 #pragma unroll
-                    for (int oc = 0; oc < kOC; ++oc)
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
-                                const float w = p.conv_w[oc * 27 + ch * 9 + dy * 3 + dx];
-                                const unsigned long long w2 = pack2(w, w);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    acc2[oc][j] = fma2(w2, dx == 0 ? E2[dy][j] : (dx == 1 ? O2[dy][j] : E2[dy][j + 1]), acc2[oc][j]);
+                                for (int px = 0; px < 8; ++px) acc2[op][px] = fma2(pack2(e[px + dx], e[px + dx]), w2, acc2[op][px]);
                             }
-                }
+                    }
 #endif
 #pragma unroll
-                for (int oc = 0; oc < kOC; ++oc, ++it) {
-                    float acc[8];
+                for (int g = 0; g < kStagesPerChunk; ++g, ++it) {
+                    uint32_t hi[kG][8], lo[kG][8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) unpack2(acc2[oc][j], acc[2 * j], acc[2 * j + 1]);
-                    uint32_t hi[8], lo[8];
+                    for (int og = 0; og < kG; ++og) {
+                        const int oc = g * kG + og;
+                        float acc[8];
 #pragma unroll
-                    for (int px = 0; px < 8; ++px) {                           // (padding pixels meet zero weights: no masking)
-                        const float a = fmaxf(acc[px], acc[px] * p.slope);     // LeakyReLU for 0 <= slope <= 1 (checked at create)
-                        hi[px] = to_tf32(a);                                   // round-to-nearest tf32: exactly what the tensor core will read
-                        lo[px] = __float_as_uint(a - __uint_as_float(hi[px])); // exact in fp32, |lo| <= 2^-11 |a|; the tensor core keeps its top 10 bits
+                        for (int px = 0; px < 8; ++px) {
+                            float c0, c1;
+                            unpack2(acc2[oc >> 1][px], c0, c1);
+                            acc[px] = (oc & 1) ? c1 : c0;
+                        }
+#pragma unroll
+                        for (int px = 0; px < 8; ++px) {                       // (padding pixels meet zero weights: no masking)
+                            const float a = fmaxf(acc[px], acc[px] * p.slope); // LeakyReLU for 0 <= slope <= 1 (checked at create)
+                            hi[og][px] = to_tf32(a);                           // round-to-nearest tf32: exactly what the tensor core will read
+                            lo[og][px] = __float_as_uint(a - __uint_as_float(hi[og][px]));   // exact in fp32, |lo| <= 2^-11 |a|; the tensor core keeps its top 10 bits
+                        }
                     }
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);               // the MMAs that read this slot have completed
-                    uint8_t* a_hi = smem + s * kAStageBytes + (r >> 3) * 512 + (r & 7) * 16 + strip * 256;
+                    uint8_t* a_hi = smem + s * kAStageBytes + (r >> 3) * kASbo + (r & 7) * 16 + strip * 256;
                     uint8_t* a_lo = a_hi + kABytes;
-                    *reinterpret_cast<uint4*>(a_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(a_hi + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    *reinterpret_cast<uint4*>(a_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(a_lo + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+#pragma unroll
+                    for (int og = 0; og < kG; ++og) {                          // k' = og * 16 + strip * 8 + px -> core (k' / 4), 128 B apart
+                        *reinterpret_cast<uint4*>(a_hi + og * 512) = make_uint4(hi[og][0], hi[og][1], hi[og][2], hi[og][3]);
+                        *reinterpret_cast<uint4*>(a_hi + og * 512 + 128) = make_uint4(hi[og][4], hi[og][5], hi[og][6], hi[og][7]);
+                        *reinterpret_cast<uint4*>(a_lo + og * 512) = make_uint4(lo[og][0], lo[og][1], lo[og][2], lo[og][3]);
+                        *reinterpret_cast<uint4*>(a_lo + og * 512 + 128) = make_uint4(lo[og][4], lo[og][5], lo[og][6], lo[og][7]);
+                    }
 #ifndef FE_DIAG_NOFENCE
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> tensor-core reads
 #endif
@@ -342,7 +371,7 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
         uint32_t it = 0, item_n = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
             const int tile = item / p.split, part = item - tile * p.split;
-            const int stages_here = ((part + 1) * p.n_chunks / p.split - part * p.n_chunks / p.split) * kOC;
+            const int stages_here = ((part + 1) * p.n_chunks / p.split - part * p.n_chunks / p.split) * kStagesPerChunk;
             if (item_n > 0) mbar_wait_relaxed(smem_u32(&bar_tmem_empty), (item_n - 1) & 1u);   // the epilogue has drained the previous item
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t used = 0;                                                 // accumulators already written in this item
@@ -357,8 +386,8 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                     const uint32_t b_hi = smem_base + kStages * kAStageBytes + sb * kBStageBytes, b_lo = b_hi + kBBytes;
 #pragma unroll
                     for (int ks = 0; ks < kStageK / 8; ++ks) {                 // one K=8 step = two 16-byte cores, 256 B further on
-                        const uint64_t dah = umma_desc(a_hi + ks * 256, 128, 512), dal = umma_desc(a_lo + ks * 256, 128, 512);
-                        const uint64_t dbh = umma_desc(b_hi + ks * 256, 128, 512), dbl = umma_desc(b_lo + ks * 256, 128, 512);
+                        const uint64_t dah = umma_desc(a_hi + ks * 256, 128, kASbo), dal = umma_desc(a_lo + ks * 256, 128, kASbo);
+                        const uint64_t dbh = umma_desc(b_hi + ks * 256, 128, kBSbo), dbl = umma_desc(b_lo + ks * 256, 128, kBSbo);
                         // the tensor core truncates when it aligns a product sum with the running accumulator, so the error
                         // grows with the number of MMAs chained on one accumulator: the hi*hi steps rotate over 15
                         // accumulators, the (2^-11 smaller) lo terms have their own; the epilogue adds the 16 partial sums
@@ -383,13 +412,13 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
             uint32_t it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int part = item % p.split;
-                const int st_begin = (part * p.n_chunks / p.split) * kOC, st_end = ((part + 1) * p.n_chunks / p.split) * kOC;
+                const int st_begin = (part * p.n_chunks / p.split) * kStagesPerChunk, st_end = ((part + 1) * p.n_chunks / p.split) * kStagesPerChunk;
                 for (int st = st_begin; st < st_end; ++st, ++it) {
                     const uint32_t sb = it % kBStages, phb = (it / kBStages) & 1u;
                     mbar_wait_relaxed(smem_u32(&bar_bempty[sb]), phb ^ 1u);
                     const uint32_t full = smem_u32(&bar_bfull[sb]);
                     mbar_arrive_expect_tx(full, kBStageBytes);
-                    tma_load_2d(smem_base + kStages * kAStageBytes + sb * kBStageBytes, &wmap, full, 0, st * 4);   // 4 rows of 256 floats = hi + lo
+                    tma_load_2d(smem_base + kStages * kAStageBytes + sb * kBStageBytes, &wmap, full, 0, st * 4 * kG);   // 4 kG rows of 256 floats = hi + lo
                 }
             }
         }
@@ -445,31 +474,38 @@ int ssd_frontend_create(int32_t view, const float* conv_w, const float* conv_b, 
     *out = nullptr;
     if (!conv_w || !conv_b || !fc_w || !fc_b || view < 1 || view > 31) return SSD_ERR_INVALID;
     if (!(negative_slope >= 0.0f && negative_slope <= 1.0f)) return SSD_ERR_INVALID;              // LeakyReLU as max(x, slope x)
-    const int N = 2 * view + 1, P = N - 2, XB = (P + 15) / 16, n_chunks = P * XB, stages = n_chunks * kOC;
+    const int N = 2 * view + 1, P = N - 2, XB = (P + 15) / 16, n_chunks = P * XB, stages = n_chunks * kStagesPerChunk;
     ssd_frontend* f = new (std::nothrow) ssd_frontend;
     if (!f) return SSD_ERR_INVALID;
     memset(f, 0, sizeof(*f));
     FrontParams& p = f->fp;
-    for (int i = 0; i < kOC * 27; ++i) p.conv_w[i] = conv_w[i] * (1.0f / 256.0f);    // exact: get_obs() = u8 / 256 (map_env.py:943)
+    for (int op = 0; op < kOC / 2; ++op)
+        for (int t = 0; t < 27; ++t) {                                                // exact scaling: get_obs() = u8 / 256 (map_env.py:943)
+            const float w0 = conv_w[(2 * op) * 27 + t] * (1.0f / 256.0f), w1 = conv_w[(2 * op + 1) * 27 + t] * (1.0f / 256.0f);
+            uint32_t b0, b1;
+            memcpy(&b0, &w0, 4); memcpy(&b1, &w1, 4);
+            p.conv_w2[op][t] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
+        }
     for (int i = 0; i < kOC; ++i) p.conv_b[i] = conv_b[i];
     for (int i = 0; i < kFeat; ++i) p.fc_b[i] = fc_b[i];
     p.slope = negative_slope; p.N = N; p.P = P; p.XB = XB; p.n_chunks = n_chunks;
     f->view = view; f->device = device;
 
     // FC weights, permuted to k' and laid out per stage exactly as the shared-memory image the tensor core reads:
-    // element (n, kk) of a [32 x 16] tile at float offset (n/8)*128 + (kk/4)*32 + (n%8)*4 + kk%4 ; hi image then lo image.
-    std::vector<float> packed((size_t)stages * 1024, 0.f);
+    // element (n, kk) of a [32 x 16 kG] tile at float offset (n/8)*128 kG + (kk/4)*32 + (n%8)*4 + kk%4 ; hi image then lo image.
+    const size_t stage_floats = 1024 * (size_t)kG, lo_off = 512 * (size_t)kG;
+    std::vector<float> packed((size_t)stages * stage_floats, 0.f);
     for (int st = 0; st < stages; ++st) {
-        const int c = st / kOC, oc = st % kOC, y = c / XB, xb = c % XB;
+        const int c = st / kStagesPerChunk, g = st % kStagesPerChunk, xb = c / P, y = c % P;   // chunks run down a column
         for (int n = 0; n < kFeat; ++n)
             for (int kk = 0; kk < kStageK; ++kk) {
-                const int x = xb * 16 + kk;
+                const int oc = g * kG + kk / 16, x = xb * 16 + kk % 16;
                 if (x >= P) continue;
                 const float w = fc_w[(size_t)n * (kOC * P * P) + (size_t)oc * P * P + y * P + x];   // nn.Linear.weight [32][6 P^2], Flatten order (oc, y, x)
                 const float hi = host_tf32(w);
-                const size_t off = (size_t)st * 1024 + (n / 8) * 128 + (kk / 4) * 32 + (n % 8) * 4 + kk % 4;
+                const size_t off = (size_t)st * stage_floats + (n / 8) * 128 * kG + (kk / 4) * 32 + (n % 8) * 4 + kk % 4;
                 packed[off] = hi;
-                packed[off + 512] = host_tf32(w - hi);
+                packed[off + lo_off] = host_tf32(w - hi);
             }
     }
     int prev = -1;
@@ -489,9 +525,9 @@ int ssd_frontend_create(int32_t view, const float* conv_w, const float* conv_b, 
         e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
         if (e == cudaSuccess && (!fn || qres != cudaDriverEntryPointSuccess)) rc = SSD_ERR_CUDA;
         if (e == cudaSuccess && rc == SSD_OK) {
-            const cuuint64_t dims[2] = { 256, (cuuint64_t)stages * 4 };
+            const cuuint64_t dims[2] = { 256, (cuuint64_t)stages * 4 * kG };
             const cuuint64_t strides[1] = { 1024 };
-            const cuuint32_t box[2] = { 256, 4 };
+            const cuuint32_t box[2] = { 256, 4 * kG };
             const cuuint32_t estr[2] = { 1, 1 };
             const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&f->wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, f->d_w, dims, strides, box, estr,
                                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
