@@ -7,18 +7,22 @@
 // so the fp32 observation (3.4x the bytes the env kernel just wrote) never exists.
 //
 // One persistent CTA per SM works on tiles of 128 agent views (GEMM rows):
-//   * warps 0-7  PRODUCERS: conv3x3 + LeakyReLU on the CUDA cores, straight from the u8 planes (27 aligned 32-bit loads give
-//                a 3x3x10 byte patch; 6 output channels x 8 pixels = 1296 FMAs per patch, issued as 648 packed fp32-pair
-//                FMAs -- fma.rn.f32x2, SASS FFMA2, new on sm_100 -- with the conv weight as broadcast scalar operand).  The activations are the A operand of the FC contraction: each thread
-//                writes its 8 values of one output channel, split as tf32 hi + lo, into the K-major core-matrix layout the
-//                tensor core reads (no swizzle: 8 rows x 16 B cores, LBO 128 B, SBO 512 B);
-//   * warp 9     TMA: the FC weight tile of the stage ([32 x 16] hi + lo, pre-packed on the host in the same core-matrix
+//   * warps 0-7  PRODUCERS: conv3x3 + LeakyReLU on the CUDA cores, straight from the u8 planes (a rolling window of 3 rows x
+//                3 planes x 3 aligned 32-bit words = a 3x3x10 byte patch, one new row per chunk; 6 output channels x 8 pixels
+//                = 1296 FMAs per patch, issued as 648 packed fp32-pair FMAs -- fma.rn.f32x2, SASS FFMA2, new on sm_100 -- on
+//                two output channels at a time: pixel as broadcast scalar, weight pair in a uniform register pair).  The
+//                activations are the A operand of the FC contraction: each thread writes its 8 values of an output channel,
+//                split as tf32 hi + lo, into the K-major core-matrix layout the tensor core reads (no swizzle: 8 rows x 16 B
+//                cores, LBO 128 B, SBO 1536 B);
+//   * warp 9     TMA: the FC weight tile of the stage ([32 x 48] hi + lo, pre-packed on the host in the same core-matrix
 //                layout) arrives with one cp.async.bulk.tensor.2d (SASS UTMALDG) on the stage's full-barrier;
 //   * warp 8     MMA: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=32, K=8), 16 accumulators in TMEM (512 columns);
 //   * warps 0-3  EPILOGUE after the last stage of a tile: tcgen05.ld (SASS LDTM) -> + bias -> LeakyReLU -> 128-bit stores.
-// A stage is one (pixel row y, 16-pixel block, output channel): A 128 x 16 (hi, lo: 16 KB) + B 32 x 16 (hi, lo: 4 KB).  The
-// activations go through a ring of 6 slots, the weight tiles through their own ring of 16 (the TMA runs two chunks ahead), so
-// the conv of the next channels overlaps the contraction of the previous ones and no stage waits for an L2 round trip.
+// A chunk is one (16-pixel column block xb, pixel row y) of the conv output, all 6 channels; a stage is half a chunk (3 output
+// channels): A 128 x 48 (hi, lo: 48 KB) + B 32 x 48 (hi, lo: 12 KB).  The activations go through a ring of 2 slots (one chunk),
+// the weight tiles through their own ring of 4 (the TMA runs two chunks ahead), so the conv of the next chunk overlaps the
+// contraction of the previous one and no stage waits for an L2 round trip.  (Stages of one channel in a ring of 6 cost a
+// hand-off per channel: 321 us instead of 255 us at V=15, profiles/r2_notes.md.)
 //
 // Precision: the reference computes in fp32.  tf32 operands keep 10 mantissa bits, so both operands are split a = hi + lo
 // with hi = rn_tf32(a) and lo = rn_tf32(a - hi) (a - hi is exact in fp32, |lo| <= 2^-11 |a|), and the contraction is
@@ -29,7 +33,7 @@
 // get their own, and the epilogue adds the partial sums in fp32.  tests/test_gpu_frontend.py states the tolerance against
 // torch fp32 and fp64.
 //
-// K is permuted (we own the packed weight format): k' = ((y * XB + xb) * 6 + oc) * 16 + px  <->  reference flatten index
+// K is permuted (we own the packed weight format): k' = ((xb * P + y) * 6 + oc) * 16 + px  <->  reference flatten index
 // k = oc * P^2 + y * P + 16 xb + px  (P = N - 2; pixels beyond P are padding: zero weights, zero activations).
 #include <cuda_runtime.h>
 #include <cuda.h>
@@ -52,6 +56,9 @@ constexpr int kTileM = 128;                  // agent views per tile
 #ifndef FE_STAGES
 #define FE_STAGES 2
 #endif
+#ifndef FE_TMA_SLEEP
+#define FE_TMA_SLEEP 64
+#endif
 #ifndef FE_BSTAGES
 #define FE_BSTAGES 4
 #endif
@@ -73,19 +80,26 @@ constexpr int kThreads = kProducerThreads + 64;        // + MMA warp + TMA warp
 constexpr int kAccs = 16;                                // independent fp32 accumulators in TMEM (see `Precision`)
 constexpr uint32_t kTmemCols = kAccs * kFeat;          // 512 columns: the whole TMEM of the SM (one CTA per SM)
 
+struct EpilogueParams {                      // what segment_epilogue needs, passed to it by value
+    long long rows;
+    long long units;                         // n_tiles * n_chunks (< 2^31); CTA i of G works on units [i units / G, (i + 1) units / G)
+    float* out;
+    float* scratch;                          // [2 G][128][32] partial sums of the tiles a CTA shares with its neighbours
+    int* tile_arrivals;                      // [n_tiles] zero between launches: partial segments stored so far
+    const float* fc_b;                       // [32] in device memory
+    int n_chunks;
+    float slope;
+};
+
 struct FrontParams {
     unsigned long long conv_w2[kOC / 2][27]; // [oc pair][ch][dy][dx] = (w[2 op], w[2 op + 1]) as packed fp32, pre-scaled by 1/256
                                              // (exact): the conv sees raw bytes
     float conv_b[kOC];
-    float fc_b[kFeat];
     float slope;
     int N, P, RP, PS, AS, XB, n_chunks;      // obs geometry; chunks per tile = P * XB
-    long long rows;
     int n_tiles;
-    int split;                               // a tile's chunks are divided among `split` work items (split-K) for load balance
     const uint8_t* obs;
-    float* out;
-    float* scratch;                          // [split][rows][32] partial sums when split > 1 (finalised by a second kernel)
+    EpilogueParams epi;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,13 +122,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
 }
+template <int kSleepNs = 64>
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {   // single-lane roles: poll, sleep, poll ...
     for (;;) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
-        __nanosleep(64);                     // leave the issue slots to the producer warps
+        __nanosleep(kSleepNs);               // leave the issue slots to the producer warps
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -126,13 +141,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+// The MMA warp runs its loop warp-uniformly and only the issue instructions are predicated on the elected lane: descriptors and
+// addresses then live in uniform registers, which is what UTCHMMA reads (inside an `if (lane == 0)` block they are computed in
+// vector registers and moved over with ~15 R2UR per K step -- and the issue rate of this lane is on the critical path).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t elected) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t elected) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(bar), "r"(elected) : "memory");
 }
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
@@ -164,6 +189,111 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int b) {
     return __uint_as_float(v) - 8388608.0f;
 }
 
+// hi*hi accumulators a segment of `stages` stages rotates over: chains of at most ~24 MMAs each (see `Precision`), at most 15
+__device__ __forceinline__ int rotation(int stages) {
+#ifdef FE_ROT_FIXED
+    return kAccs - 1;
+#else
+    const int steps = stages * (kStageK / 8);
+    return min(kAccs - 1, (steps + 23) / 24);
+#endif
+}
+
+// Epilogue of one segment, by warps 0-3 (TMEM lane = GEMM row = r).  Kept out of line so that its 32 + 32 live registers do not
+// weigh on the register allocation of the convolution loop.
+#ifdef FE_INLINE_EPI
+#define FE_EPI_INLINE __forceinline__
+#else
+#define FE_EPI_INLINE __noinline__
+#endif
+__device__ FE_EPI_INLINE void segment_epilogue(const EpilogueParams p, uint32_t tmem_base, uint32_t bar_tmem_full, uint32_t bar_tmem_empty,
+                                          int* arrivals_s, uint32_t parity, int stages_here, int tile, bool whole_tile,
+                                          bool first_segment) {
+    const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127;
+    const long long row = (long long)tile * kTileM + r;
+    mbar_wait(bar_tmem_full, parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float sum[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // the partial sums are added smallest first (accumulator 0 holds the lo terms), in fp32 round-to-nearest
+    const int n_acc = 1 + rotation(stages_here);                   // short segments use fewer than 16
+    for (int a = 0; a < n_acc; ++a) {
+        uint32_t v[32];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr + (uint32_t)(a * kFeat)) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(bar_tmem_empty);                                   // the accumulator may be overwritten by the next tile
+    if (!whole_tile) {
+        // A tile shared with neighbouring CTAs: raw partial sums go to this CTA's scratch slot (2 i for the tile it
+        // starts in, 2 i + 1 for the tile it ends in); the CTA that stores the tile's LAST part adds all parts in CTA
+        // order -- so the result does not depend on which CTA that is -- and writes the output.
+        const int slot = 2 * blockIdx.x + (first_segment ? 0 : 1);
+        float4* dst = reinterpret_cast<float4*>(p.scratch + ((long long)slot * kTileM + r) * kFeat);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) __stcg(dst + j, make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]));
+        // CTA that holds unit X: ceil((X + 1) G / U) - 1, because CTA i starts at floor(i U / G)
+        const long long x0 = (long long)tile * p.n_chunks, x1 = x0 + p.n_chunks - 1, G = gridDim.x;
+        const int i0 = (int)(((x0 + 1) * G + p.units - 1) / p.units) - 1, i1 = (int)(((x1 + 1) * G + p.units - 1) / p.units) - 1;
+        __threadfence();                                            // this thread's part is visible device-wide ...
+        asm volatile("bar.sync 1, 128;" ::: "memory");              // ... and so is every epilogue thread's
+        if (tid == 0) *arrivals_s = atomicAdd(p.tile_arrivals + tile, 1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*arrivals_s == i1 - i0) {                                // the other i1 - i0 parts were stored before this one
+            __threadfence();
+            if (tid == 0) p.tile_arrivals[tile] = 0;                // ready for the next launch
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+            for (int i = i0; i <= i1; ++i) {
+                const int b = (int)((long long)i * p.units / G);
+                const int sl = 2 * i + (b >= x0 ? 0 : 1);           // b_i <= x1 for every CTA of this tile
+                const float4* src = reinterpret_cast<const float4*>(p.scratch + ((long long)sl * kTileM + r) * kFeat);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = __ldcg(src + j);
+                    sum[4 * j] += v.x; sum[4 * j + 1] += v.y; sum[4 * j + 2] += v.z; sum[4 * j + 3] += v.w;
+                }
+            }
+            if (row < p.rows) {
+                float4* o4 = reinterpret_cast<float4*>(p.out + row * kFeat);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.fc_b) + j);
+                    float4 o;
+                    o.x = leaky(sum[4 * j + 0] + b4.x, p.slope);
+                    o.y = leaky(sum[4 * j + 1] + b4.y, p.slope);
+                    o.z = leaky(sum[4 * j + 2] + b4.z, p.slope);
+                    o.w = leaky(sum[4 * j + 3] + b4.w, p.slope);
+                    o4[j] = o;
+                }
+            }
+        }
+    } else if (row < p.rows) {
+        float4* dst = reinterpret_cast<float4*>(p.out + row * kFeat);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.fc_b) + j);
+            float4 o;
+            o.x = leaky(sum[4 * j + 0] + b4.x, p.slope);
+            o.y = leaky(sum[4 * j + 1] + b4.y, p.slope);
+            o.z = leaky(sum[4 * j + 2] + b4.z, p.slope);
+            o.w = leaky(sum[4 * j + 3] + b4.w, p.slope);
+            dst[j] = o;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ CUtensorMap wmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -173,6 +303,7 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
     __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_bfull[kBStages], bar_bempty[kBStages],
                                      bar_tmem_full, bar_tmem_empty;
     __shared__ uint32_t tmem_base_s;
+    __shared__ int arrivals_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -191,7 +322,10 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t smem_base = smem_u32(smem);
-    const int n_items = p.n_tiles * p.split;
+    // Work division ("stream-K"): all (tile, chunk) units in one sequence, an equal contiguous share per CTA.  A share is cut at
+    // tile boundaries into segments; a segment that covers a whole tile stores the finished output, a partial one stores raw
+    // partial sums, and the last of a tile's CTAs to do so adds them up.  Every role walks the same segments.
+    const int u_begin = (int)((long long)blockIdx.x * p.epi.units / gridDim.x), u_end = (int)((long long)(blockIdx.x + 1) * p.epi.units / gridDim.x);
 
     if (warp < 8) {
         // ------------------------------------------------------------------ producers (+ epilogue on warps 0-3)
@@ -200,9 +334,11 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
         unsigned long long bias2[kOC / 2];
 #pragma unroll
         for (int op = 0; op < kOC / 2; ++op) bias2[op] = pack2(p.conv_b[2 * op], p.conv_b[2 * op + 1]);
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            const int tile = item / p.split, part = item - tile * p.split;
-            const int c_begin = part * p.n_chunks / p.split, c_end = (part + 1) * p.n_chunks / p.split;
+        for (int u = u_begin; u < u_end; ++item_n) {
+            const int tile = u / p.n_chunks, c_begin = u - tile * p.n_chunks;
+            const int c_end = min(p.n_chunks, c_begin + (u_end - u));
+            const bool first_segment = u == u_begin;
+            u += c_end - c_begin;
             const int stages_here = (c_end - c_begin) * kStagesPerChunk;
             const long long row = (long long)tile * kTileM + r;
             // Chunks run down a 16-pixel column (c = xb * P + y), so consecutive chunks share two of their three patch rows: the
@@ -210,7 +346,7 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
             // before the current chunk is convolved, so its L2 latency hides behind the FMAs.  (A shared-memory row window filled
             // with coalesced loads was measured and dropped: the per-row CTA barrier cost more than the sectors it saved --
             // V=15: 515 us instead of 397 us, profiles/r2_notes.md.)
-            const long long row_ld = row < p.rows ? row : p.rows - 1;          // partial last tile: compute on a valid row, never store
+            const long long row_ld = row < p.epi.rows ? row : p.epi.rows - 1;          // partial last tile: compute on a valid row, never store
             const uint8_t* view = p.obs + row_ld * p.AS;
             uint32_t win[3][9], nxt[9];
             auto load_row = [&](uint32_t (&dst)[9], int yy, int xb) {
@@ -273,13 +409,14 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                         e[8] = byte_to_float(cur[k + 2], 0);
                         e[9] = byte_to_float(cur[k + 2], 1);
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx)
+                        for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
                             for (int op = 0; op < kOC / 2; ++op) {
                                 const unsigned long long w2 = p.conv_w2[op][ch * 9 + dy * 3 + dx];
 #pragma unroll
                                 for (int px = 0; px < 8; ++px) acc2[op][px] = fma2(pack2(e[px + dx], e[px + dx]), w2, acc2[op][px]);
                             }
+                        }
                     }
 #endif
 #pragma unroll
@@ -297,15 +434,22 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                         }
 #pragma unroll
                         for (int px = 0; px < 8; ++px) {                       // (padding pixels meet zero weights: no masking)
+#ifdef FE_DIAG_NOEPI
+                            hi[og][px] = __float_as_uint(acc[px]) & 0xffffe000u; lo[og][px] = 0u;
+#else
                             const float a = fmaxf(acc[px], acc[px] * p.slope); // LeakyReLU for 0 <= slope <= 1 (checked at create)
                             hi[og][px] = to_tf32(a);                           // round-to-nearest tf32: exactly what the tensor core will read
                             lo[og][px] = __float_as_uint(a - __uint_as_float(hi[og][px]));   // exact in fp32, |lo| <= 2^-11 |a|; the tensor core keeps its top 10 bits
+#endif
                         }
                     }
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);               // the MMAs that read this slot have completed
                     uint8_t* a_hi = smem + s * kAStageBytes + (r >> 3) * kASbo + (r & 7) * 16 + strip * 256;
                     uint8_t* a_lo = a_hi + kABytes;
+#ifdef FE_DIAG_NOSTS
+                    if (hi[0][0] == 0x12345u && lo[kG - 1][7] == 0x54321u)
+#endif
 #pragma unroll
                     for (int og = 0; og < kG; ++og) {                          // k' = og * 16 + strip * 8 + px -> core (k' / 4), 128 B apart
                         *reinterpret_cast<uint4*>(a_hi + og * 512) = make_uint4(hi[og][0], hi[og][1], hi[og][2], hi[og][3]);
@@ -320,102 +464,68 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                     if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
                 }
             }
-            if (warp < 4) {
-                // -------------------------------------------------------------- epilogue: TMEM lane = GEMM row = r
-                mbar_wait(smem_u32(&bar_tmem_full), item_n & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                float sum[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum[j] = 0.f;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-                // the partial sums are added smallest first (accumulator 0 holds the lo terms), in fp32 round-to-nearest
-                const int n_acc = min(kAccs, 1 + stages_here * (kStageK / 8));       // short items use fewer than 16
-                for (int a = 0; a < n_acc; ++a) {
-                    uint32_t v[32];
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                                 : "r"(taddr + (uint32_t)(a * kFeat)) : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(smem_u32(&bar_tmem_empty));                        // the accumulator may be overwritten by the next tile
-                if (row < p.rows && p.split > 1) {                              // partial sums; bias and activation in finalize
-                    float4* dst = reinterpret_cast<float4*>(p.scratch + ((long long)part * p.rows + row) * kFeat);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
-                } else if (row < p.rows) {
-                    float4* dst = reinterpret_cast<float4*>(p.out + row * kFeat);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o;
-                        o.x = leaky(sum[4 * j + 0] + p.fc_b[4 * j + 0], p.slope);
-                        o.y = leaky(sum[4 * j + 1] + p.fc_b[4 * j + 1], p.slope);
-                        o.z = leaky(sum[4 * j + 2] + p.fc_b[4 * j + 2], p.slope);
-                        o.w = leaky(sum[4 * j + 3] + p.fc_b[4 * j + 3], p.slope);
-                        dst[j] = o;
-                    }
-                }
-            }
+            if (warp < 4)
+                segment_epilogue(p.epi, tmem_base, smem_u32(&bar_tmem_full), smem_u32(&bar_tmem_empty), &arrivals_s, item_n & 1u, stages_here,
+                                 tile, c_end - c_begin == p.n_chunks, first_segment);
         }
     } else if (warp == 8) {
         // ---------------------------------------------------------------------- MMA issuer (one elected lane)
         // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 32, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kFeat >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        const uint32_t elected = elect_one();
         uint32_t it = 0, item_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            const int tile = item / p.split, part = item - tile * p.split;
-            const int stages_here = ((part + 1) * p.n_chunks / p.split - part * p.n_chunks / p.split) * kStagesPerChunk;
+        for (int u = u_begin; u < u_end; ++item_n) {
+            const int c_begin = u % p.n_chunks;
+            const int c_end = min(p.n_chunks, c_begin + (u_end - u));
+            u += c_end - c_begin;
+            const int stages_here = (c_end - c_begin) * kStagesPerChunk;
             if (item_n > 0) mbar_wait_relaxed(smem_u32(&bar_tmem_empty), (item_n - 1) & 1u);   // the epilogue has drained the previous item
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t used = 0;                                                 // accumulators already written in this item
+            // the tensor core truncates when it aligns a product sum with the running accumulator, so the error grows with the
+            // number of MMAs chained on one accumulator: the hi*hi steps rotate over up to 15 accumulators, the (2^-11 smaller)
+            // lo terms have their own; the epilogue adds the partial sums
+            const uint32_t n_rot = (uint32_t)rotation(stages_here);
+            uint32_t acc = 1;
             for (int st = 0; st < stages_here; ++st, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                 const uint32_t sb = it % kBStages, phb = (it / kBStages) & 1u;
                 mbar_wait(smem_u32(&bar_bfull[sb]), phb);                      // weight tile landed (TMA, issued well ahead)
                 mbar_wait(smem_u32(&bar_full[s]), ph);                         // activations written by the 256 producers
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t a_hi = smem_base + s * kAStageBytes, a_lo = a_hi + kABytes;
-                    const uint32_t b_hi = smem_base + kStages * kAStageBytes + sb * kBStageBytes, b_lo = b_hi + kBBytes;
+                const uint32_t a_hi = smem_base + s * kAStageBytes, b_hi = smem_base + kStages * kAStageBytes + sb * kBStageBytes;
+                uint64_t dah = umma_desc(a_hi, 128, kASbo), dal = umma_desc(a_hi + kABytes, 128, kASbo);
+                uint64_t dbh = umma_desc(b_hi, 128, kBSbo), dbl = umma_desc(b_hi + kBBytes, 128, kBSbo);
 #pragma unroll
-                    for (int ks = 0; ks < kStageK / 8; ++ks) {                 // one K=8 step = two 16-byte cores, 256 B further on
-                        const uint64_t dah = umma_desc(a_hi + ks * 256, 128, kASbo), dal = umma_desc(a_lo + ks * 256, 128, kASbo);
-                        const uint64_t dbh = umma_desc(b_hi + ks * 256, 128, kBSbo), dbl = umma_desc(b_lo + ks * 256, 128, kBSbo);
-                        // the tensor core truncates when it aligns a product sum with the running accumulator, so the error
-                        // grows with the number of MMAs chained on one accumulator: the hi*hi steps rotate over 15
-                        // accumulators, the (2^-11 smaller) lo terms have their own; the epilogue adds the 16 partial sums
-                        const uint32_t acc = 1u + (uint32_t)(st * (kStageK / 8) + ks) % (kAccs - 1);
-                        umma_tf32(tmem_base + acc * kFeat, dah, dbh, idesc, (used >> acc) & 1u);
-#ifndef FE_DIAG_HIONLY                                                  // diagnostic build: one MMA per K step instead of three
-                        umma_tf32(tmem_base, dal, dbh, idesc, used & 1u);
-                        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                for (int ks = 0; ks < kStageK / 8; ++ks) {                     // one K=8 step = two 16-byte cores, 256 B further on
+#ifndef FE_DIAG_NOMMA
+                    umma_tf32(tmem_base + acc * kFeat, dah, dbh, idesc, (used >> acc) & 1u, elected);
 #endif
-                        used |= 1u | (1u << acc);
-                    }
-                    umma_commit(smem_u32(&bar_empty[s]));                      // frees both slots when these MMAs have read them
-                    umma_commit(smem_u32(&bar_bempty[sb]));
-                    if (st == stages_here - 1) umma_commit(smem_u32(&bar_tmem_full));
+#if !defined(FE_DIAG_HIONLY) && !defined(FE_DIAG_NOMMA)                        // diagnostic build: one MMA per K step instead of three
+                    umma_tf32(tmem_base, dal, dbh, idesc, used & 1u, elected);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1u, elected);
+#endif
+                    used |= 1u | (1u << acc);
+                    acc = acc == n_rot ? 1u : acc + 1u;
+                    dah += 256 >> 4; dal += 256 >> 4; dbh += 256 >> 4; dbl += 256 >> 4;   // the address field counts 16-byte units
                 }
-                __syncwarp();
+                umma_commit(smem_u32(&bar_empty[s]), elected);                 // frees both slots when these MMAs have read them
+                umma_commit(smem_u32(&bar_bempty[sb]), elected);
+                if (st == stages_here - 1) umma_commit(smem_u32(&bar_tmem_full), elected);
             }
         }
     } else {
         // ---------------------------------------------------------------------- TMA: FC weight tile of every stage
         if (lane == 0) {
             uint32_t it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int part = item % p.split;
-                const int st_begin = (part * p.n_chunks / p.split) * kStagesPerChunk, st_end = ((part + 1) * p.n_chunks / p.split) * kStagesPerChunk;
+            for (int u = u_begin; u < u_end;) {
+                const int c_begin = u % p.n_chunks;
+                const int c_end = min(p.n_chunks, c_begin + (u_end - u));
+                u += c_end - c_begin;
+                const int st_begin = c_begin * kStagesPerChunk, st_end = c_end * kStagesPerChunk;
                 for (int st = st_begin; st < st_end; ++st, ++it) {
                     const uint32_t sb = it % kBStages, phb = (it / kBStages) & 1u;
-                    mbar_wait_relaxed(smem_u32(&bar_bempty[sb]), phb ^ 1u);
+                    mbar_wait_relaxed<FE_TMA_SLEEP>(smem_u32(&bar_bempty[sb]), phb ^ 1u);
                     const uint32_t full = smem_u32(&bar_bfull[sb]);
                     mbar_arrive_expect_tx(full, kBStageBytes);
                     tma_load_2d(smem_base + kStages * kAStageBytes + sb * kBStageBytes, &wmap, full, 0, st * 4 * kG);   // 4 kG rows of 256 floats = hi + lo
@@ -427,22 +537,6 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(kTmemCols) : "memory");
-}
-
-// split-K epilogue: out = LeakyReLU(bias + sum over parts, in part order), one thread per output float4
-__global__ void frontend_finalize_kernel(const float* __restrict__ scratch, float* __restrict__ out, long long rows, int split,
-                                         const __grid_constant__ FrontParams p) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
-    if (i >= rows * (kFeat / 4)) return;
-    const int j = (int)(i % (kFeat / 4)) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < split; ++s) {
-        const float4 v = reinterpret_cast<const float4*>(scratch + (long long)s * rows * kFeat)[i];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    acc.x = leaky(acc.x + p.fc_b[j], p.slope); acc.y = leaky(acc.y + p.fc_b[j + 1], p.slope);
-    acc.z = leaky(acc.z + p.fc_b[j + 2], p.slope); acc.w = leaky(acc.w + p.fc_b[j + 3], p.slope);
-    reinterpret_cast<float4*>(out)[i] = acc;
 }
 
 thread_local int g_front_cuda_error = 0;
@@ -459,9 +553,10 @@ inline float host_tf32(float v) {                              // cvt.rna.tf32.f
 struct ssd_frontend {
     FrontParams fp;
     CUtensorMap wmap;
-    float* d_w;                                                // packed FC weights: [stages][hi 512 | lo 512] floats
-    float* d_scratch;                                          // split-K partial sums, grown on demand
-    size_t scratch_floats;
+    float* d_w;                                                // packed FC weights: [stages][hi | lo] tiles, then the 32 bias floats
+    float* d_scratch;                                          // partial sums of shared tiles: [2 sms][128][32]
+    int* d_arrivals;                                           // [arrivals_len] per-tile counters, zero between launches
+    size_t arrivals_len;
     int device, view, sms;
     size_t smem_bytes;
 };
@@ -487,8 +582,7 @@ int ssd_frontend_create(int32_t view, const float* conv_w, const float* conv_b, 
             p.conv_w2[op][t] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
         }
     for (int i = 0; i < kOC; ++i) p.conv_b[i] = conv_b[i];
-    for (int i = 0; i < kFeat; ++i) p.fc_b[i] = fc_b[i];
-    p.slope = negative_slope; p.N = N; p.P = P; p.XB = XB; p.n_chunks = n_chunks;
+    p.slope = p.epi.slope = negative_slope; p.epi.n_chunks = n_chunks; p.N = N; p.P = P; p.XB = XB; p.n_chunks = n_chunks;
     f->view = view; f->device = device;
 
     // FC weights, permuted to k' and laid out per stage exactly as the shared-memory image the tensor core reads:
@@ -511,8 +605,11 @@ int ssd_frontend_create(int32_t view, const float* conv_w, const float* conv_b, 
     int prev = -1;
     cudaError_t e = cudaGetDevice(&prev);
     if (e == cudaSuccess && prev != device) e = cudaSetDevice(device);
+    const size_t w_floats = packed.size();
+    packed.insert(packed.end(), fc_b, fc_b + kFeat);           // the FC bias rides behind the weight tiles
     if (e == cudaSuccess) e = cudaMalloc(&f->d_w, packed.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(f->d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice);
+    p.epi.fc_b = f->d_w + w_floats;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&f->sms, cudaDevAttrMultiProcessorCount, device);
     int rc = SSD_OK;
     if (e == cudaSuccess) {
@@ -559,48 +656,44 @@ int ssd_frontend_forward(ssd_frontend* f, const uint8_t* obs, int64_t rows, int3
         (reinterpret_cast<uintptr_t>(out) & 15))
         return SSD_ERR_INVALID;
     p.RP = obs_row_stride; p.PS = obs_plane_stride; p.AS = obs_agent_stride;
-    p.rows = rows; p.n_tiles = (int)((rows + kTileM - 1) / kTileM);
-    p.obs = obs; p.out = out;
-    // split-K for load balance: 160 tiles on 148 persistent CTAs would leave a second, almost empty round.  A tile's chunks are
-    // divided among `split` work items; the factor minimises rounds x (chunks per item + ~1.5 chunks of pipeline fill and
-    // epilogue per item), which reproduces the measured optimum (profiles/r2_notes.md).  Partial sums are combined in part order
-    // by frontend_finalize_kernel, so the result does not depend on the schedule.
-    int split = 1;
+    if ((rows + kTileM - 1) / kTileM * p.n_chunks >= (1ll << 31)) return SSD_ERR_INVALID;   // the kernel counts units in 32 bits
+    p.epi.rows = rows; p.n_tiles = (int)((rows + kTileM - 1) / kTileM);
+    p.obs = obs; p.epi.out = out;
+    // Load balance: 160 tiles on 148 persistent CTAs would leave a second, almost empty round, so the (tile, chunk) units are
+    // dealt out as one sequence in equal contiguous shares (see the kernel).  Tiles cut by a share boundary are combined in CTA
+    // order by whichever CTA stores its part last, so the result does not depend on timing.  The scratch slots and arrival
+    // counters belong to the handle: one forward at a time per handle (stream order is enough).
+    const long long units = p.epi.units = (long long)p.n_tiles * p.n_chunks;
+    // Grid: all SMs with equal shares, or -- few tiles -- s CTAs per tile (shares aligned with the tiles, one segment per CTA);
+    // whichever has the cheaper busiest CTA at ~1.5 chunks of pipeline fill + accumulator drain per segment.
+    int grid = units < f->sms ? (int)units : f->sms;
     {
-        double best = 1e30;
-        const int smax = p.n_chunks < 16 ? p.n_chunks : 16;
-        for (int s_ = 1; s_ <= smax; ++s_) {
-            const long long items = (long long)p.n_tiles * s_;
-            const double rounds = (double)((items + f->sms - 1) / f->sms);
-            const double cost = rounds * ((double)p.n_chunks / s_ + 1.5);
-            if (cost < best - 1e-9) { best = cost; split = s_; }
+        const double share = (double)units / grid;
+        double best = share + 1.5 * (share < p.n_chunks ? 2.0 : (double)((long long)(share / p.n_chunks) + 2));
+        for (int s_ = 1; s_ <= p.n_chunks && (long long)p.n_tiles * s_ <= f->sms; ++s_) {
+            const double cost = (double)((p.n_chunks + s_ - 1) / s_) + 1.5;
+            if (cost < best - 1e-9) { best = cost; grid = p.n_tiles * s_; }
         }
     }
-    { const char* e_ = getenv("SSD_B200_FRONTEND_SPLIT"); if (e_ && atoi(e_) >= 1 && atoi(e_) <= p.n_chunks) split = atoi(e_); }   // tuning
-    p.split = split;
+    { const char* e_ = getenv("SSD_B200_FRONTEND_GRID"); if (e_ && atoi(e_) >= 1 && atoi(e_) <= grid) grid = atoi(e_); }   // tuning
     int prev = -1;
     cudaError_t e = cudaGetDevice(&prev);
     if (e == cudaSuccess && prev != f->device) e = cudaSetDevice(f->device);
-    if (e == cudaSuccess && split > 1) {
-        const size_t need = (size_t)split * (size_t)rows * kFeat;
-        if (need > f->scratch_floats) {                        // first call / larger batch: (re)allocate (not capturable)
-            if (f->d_scratch) cudaFree(f->d_scratch);
-            f->d_scratch = nullptr; f->scratch_floats = 0;
-            e = cudaMalloc(&f->d_scratch, need * sizeof(float));
-            if (e == cudaSuccess) f->scratch_floats = need;
-        }
-        p.scratch = f->d_scratch;
+    if (e == cudaSuccess && !f->d_scratch)                     // first call (not capturable): two partial tiles per CTA
+        e = cudaMalloc(&f->d_scratch, (size_t)2 * f->sms * kTileM * kFeat * sizeof(float));
+    if (e == cudaSuccess && (size_t)p.n_tiles > f->arrivals_len) {             // first call / larger batch (not capturable)
+        if (f->d_arrivals) cudaFree(f->d_arrivals);
+        f->d_arrivals = nullptr; f->arrivals_len = 0;
+        const size_t len = ((size_t)p.n_tiles + 1023) / 1024 * 1024;
+        e = cudaMalloc(&f->d_arrivals, len * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->d_arrivals, 0, len * sizeof(int), (cudaStream_t)stream);
+        if (e == cudaSuccess) f->arrivals_len = len;
     }
+    p.epi.scratch = f->d_scratch;
+    p.epi.tile_arrivals = f->d_arrivals;
     if (e == cudaSuccess) {
-        const int items = p.n_tiles * split;
-        const int grid = items < f->sms ? items : f->sms;
         obs_frontend_kernel<<<grid, kThreads, f->smem_bytes, (cudaStream_t)stream>>>(p, f->wmap);
         e = cudaGetLastError();
-        if (e == cudaSuccess && split > 1) {
-            const long long n4 = rows * (kFeat / 4);
-            frontend_finalize_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.scratch, out, rows, split, p);
-            e = cudaGetLastError();
-        }
     }
     if (prev >= 0 && prev != f->device) cudaSetDevice(prev);
     if (e != cudaSuccess) { g_front_cuda_error = (int)e; return SSD_ERR_CUDA; }
@@ -614,6 +707,7 @@ int ssd_frontend_destroy(ssd_frontend* f) {
     if (prev != f->device) cudaSetDevice(f->device);
     cudaFree(f->d_w);
     if (f->d_scratch) cudaFree(f->d_scratch);
+    if (f->d_arrivals) cudaFree(f->d_arrivals);
     if (prev >= 0 && prev != f->device) cudaSetDevice(prev);
     delete f;
     return SSD_OK;

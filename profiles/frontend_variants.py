@@ -9,14 +9,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "g1_s6_b16": ["-DFE_OC_PER_STAGE=1", "-DFE_STAGES=6", "-DFE_BSTAGES=16"],
-    "g2_s3_b8": ["-DFE_OC_PER_STAGE=2", "-DFE_STAGES=3", "-DFE_BSTAGES=8"],
-    "g2_s4_b8": ["-DFE_OC_PER_STAGE=2", "-DFE_STAGES=4", "-DFE_BSTAGES=8"],
-    "g3_s2_b5": ["-DFE_OC_PER_STAGE=3", "-DFE_STAGES=2", "-DFE_BSTAGES=5"],
-    "g3_s2_b4": ["-DFE_OC_PER_STAGE=3", "-DFE_STAGES=2", "-DFE_BSTAGES=4"],
-    "g3_s3_b5": ["-DFE_OC_PER_STAGE=3", "-DFE_STAGES=3", "-DFE_BSTAGES=5"],
-    "g3_s2_b5_noconv": ["-DFE_OC_PER_STAGE=3", "-DFE_STAGES=2", "-DFE_BSTAGES=5", "-DFE_DIAG_NOCONV"],
-    "g3_s2_b5_hionly": ["-DFE_OC_PER_STAGE=3", "-DFE_STAGES=2", "-DFE_BSTAGES=5", "-DFE_DIAG_HIONLY"],
+    "w0_cur": [],
+    "w1_rotfixed": ["-DFE_ROT_FIXED"],
+    "w2_nomma": ["-DFE_DIAG_NOMMA"],
+    "w3_inline": ["-DFE_INLINE_EPI"],
 }
 
 if sys.argv[1:] == ["build"]:
@@ -30,7 +26,7 @@ elif sys.argv[1:] == ["time"]:
     import torch
     from homophily_marl_b200.frontend import ObsFrontEnd
     out = {}
-    for view, rows in ((15, 20480), (7, 20480), (15, 2560)):
+    for view, rows in ((15, 20480), (15, 18944), (7, 20480), (15, 2560)):
         N = 2 * view + 1
         RP = (N + 3) // 4 * 4
         PS, AS = N * RP, (3 * N * RP + 15) // 16 * 16
@@ -56,7 +52,7 @@ else:
         r = subprocess.run(["timeout", "200", sys.executable, __file__, "time"], capture_output=True, text=True, env=env)
         res = r.stdout.strip() or ("ERR " + r.stderr[-300:])
         t = ""
-        if "noconv" not in lib and "noload" not in lib and "hionly" not in lib:
+        if "g_full" in lib and os.environ.get("FE_TESTS"):
             r = subprocess.run(["timeout", "300", sys.executable, "-m", "pytest", "tests/test_gpu_frontend.py", "-m", "gpu", "-q", "-x"],
                                capture_output=True, text=True, env=env, cwd=ROOT)
             t = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-200:]

@@ -8,6 +8,8 @@ and split-K partial sums.  Against an fp64 evaluation of the same module the ker
 0.3e-7 .. 1.2e-7, torch's own fp32 path measures 0.5e-7 .. 1.0e-6 on the same inputs -- and within 3e-6 * (1 + |y|) of torch
 fp32 on the GPU (TF32 disabled in cuDNN / cuBLAS for the comparison)."""
 import numpy as np
+import os
+
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -43,7 +45,8 @@ def _compare(fe, mod, obs_buf, rows, lay, N):
     return err64, torch_err64
 
 
-@pytest.mark.parametrize("view,rows", [(7, 1), (7, 127), (7, 128), (7, 129), (7, 20480), (15, 5), (15, 300), (15, 20480), (3, 200), (1, 130)])
+@pytest.mark.parametrize("view,rows", [(7, 1), (7, 127), (7, 128), (7, 129), (7, 20480), (15, 5), (15, 300), (15, 20480), (3, 200), (1, 130),
+                                       (7, 148 * 128), (15, 74 * 128), (15, 37 * 128 + 3)])
 def test_fused_front_end_matches_the_reference_module(view, rows):
     from homophily_marl_b200.frontend import ObsFrontEnd
     dev = torch.device("cuda:0")
@@ -56,6 +59,20 @@ def test_fused_front_end_matches_the_reference_module(view, rows):
     fe = ObsFrontEnd.from_module(mod, view, device=dev)
     err, terr = _compare(fe, mod, buf, rows, dict(AS=AS, PS=PS, RP=RP), N)
     print(f"view {view} rows {rows}: max rel err vs fp64 {err:.2e} (torch fp32: {terr:.2e})")
+    if rows == 300:                                            # the work division must not change the result beyond fp32 summation order
+        ref = fe.forward(buf, rows, AS, PS, RP).clone()
+        for grid in ("1", "2", "7", "100"):
+            os.environ["SSD_B200_FRONTEND_GRID"] = grid
+            try:
+                got = fe.forward(buf, rows, AS, PS, RP)
+                torch.cuda.synchronize()
+            finally:
+                os.environ.pop("SSD_B200_FRONTEND_GRID")
+            assert ((got - ref).abs() / (1 + ref.abs())).max().item() < 1e-6, grid
+    if rows >= 9000:                                           # shared tiles are summed in CTA order whichever CTA finishes last
+        a = fe.forward(buf, rows, AS, PS, RP).clone()
+        for _ in range(3):
+            assert torch.equal(fe.forward(buf, rows, AS, PS, RP), a)
     if rows >= 20480:                                          # informational timing: fused kernel vs the torch module on fp32 obs
         def timed(fn, reps=20):
             fn()
