@@ -16,8 +16,13 @@
 //                cores, LBO 128 B, SBO 1536 B);
 //   * warp 9     TMA: the FC weight tile of the stage ([32 x 48] hi + lo, pre-packed on the host in the same core-matrix
 //                layout) arrives with one cp.async.bulk.tensor.2d (SASS UTMALDG) on the stage's full-barrier;
-//   * warp 8     MMA: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=32, K=8), 16 accumulators in TMEM (512 columns);
-//   * warps 0-3  EPILOGUE after the last stage of a tile: tcgen05.ld (SASS LDTM) -> + bias -> LeakyReLU -> 128-bit stores.
+//   * warps 8,10 MMA: one elected lane each issues tcgen05.mma.kind::tf32 (M=128, N=32, K=8) for every other K step of a
+//                stage into its own 8 of the 16 TMEM accumulators (512 columns) -- with MMAs this small the issue rate of one
+//                lane, not the tensor core, was the limit;
+//   * warps 0-3  EPILOGUE after the last stage of a segment: tcgen05.ld (SASS LDTM) -> + bias -> LeakyReLU -> 128-bit stores.
+// Work division: the (tile, chunk) units form one sequence that is dealt out in equal contiguous shares, one per CTA; a tile
+// cut by a share boundary is combined, in CTA order, by whichever of its CTAs stores its partial sums last (one launch, result
+// independent of timing).
 // A chunk is one (16-pixel column block xb, pixel row y) of the conv output, all 6 channels; a stage is half a chunk (3 output
 // channels): A 128 x 48 (hi, lo: 48 KB) + B 32 x 48 (hi, lo: 12 KB).  The activations go through a ring of 2 slots (one chunk),
 // the weight tiles through their own ring of 4 (the TMA runs two chunks ahead), so the conv of the next chunk overlaps the
@@ -29,8 +34,8 @@
 // hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM; the dropped lo*lo term and the rounding of lo are below 2^-21 relative
 // per product.  What dominates instead is the tensor core's own accumulation: adding a K=8 product sum to the running fp32
 // accumulator truncates, and the error grows linearly with the number of MMAs chained on one accumulator (measured: 4e-6
-// relative at 468 chained MMAs, 1.5e-5 at 2088).  Hence 16 accumulators: the hi*hi steps rotate over 15 of them, the lo terms
-// get their own, and the epilogue adds the partial sums in fp32.  tests/test_gpu_frontend.py states the tolerance against
+// relative at 468 chained MMAs, 1.5e-5 at 2088).  Hence 16 accumulators: each issuer rotates its hi*hi steps over up to 7, its
+// lo terms get their own, and the epilogue adds the partial sums in fp32.  tests/test_gpu_frontend.py states the tolerance against
 // torch fp32 and fp64.
 //
 // K is permuted (we own the packed weight format): k' = ((xb * P + y) * 6 + oc) * 16 + px  <->  reference flatten index
@@ -76,7 +81,8 @@ constexpr int kSmemBytes = kStages * kAStageBytes + kBStages * kBStageBytes;
 static_assert(kOC % kG == 0, "stage must hold whole output channels");
 static_assert(kSmemBytes + 1024 <= 227 * 1024, "rings exceed shared memory");
 constexpr int kProducerThreads = 256;
-constexpr int kThreads = kProducerThreads + 64;        // + MMA warp + TMA warp
+constexpr int kIssuers = 2;                              // MMA-issuing warps (8 and 10): the issue rate of one lane was the limit
+constexpr int kThreads = kProducerThreads + 96;        // + MMA warp + TMA warp + second MMA warp
 constexpr int kAccs = 16;                                // independent fp32 accumulators in TMEM (see `Precision`)
 constexpr uint32_t kTmemCols = kAccs * kFeat;          // 512 columns: the whole TMEM of the SM (one CTA per SM)
 
@@ -189,24 +195,16 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int b) {
     return __uint_as_float(v) - 8388608.0f;
 }
 
-// hi*hi accumulators a segment of `stages` stages rotates over: chains of at most ~24 MMAs each (see `Precision`), at most 15
+// hi*hi accumulators each issuer rotates over in a segment of `stages` stages: chains of at most ~24 MMAs each (see `Precision`),
+// at most 7 (+ 1 for the lo terms) of the 8 accumulators an issuer owns
 __device__ __forceinline__ int rotation(int stages) {
-#ifdef FE_ROT_FIXED
-    return kAccs - 1;
-#else
-    const int steps = stages * (kStageK / 8);
-    return min(kAccs - 1, (steps + 23) / 24);
-#endif
+    const int steps = stages * (kStageK / 8) / kIssuers;
+    return min(kAccs / kIssuers - 1, (steps + 23) / 24);
 }
 
 // Epilogue of one segment, by warps 0-3 (TMEM lane = GEMM row = r).  Kept out of line so that its 32 + 32 live registers do not
 // weigh on the register allocation of the convolution loop.
-#ifdef FE_INLINE_EPI
-#define FE_EPI_INLINE __forceinline__
-#else
-#define FE_EPI_INLINE __noinline__
-#endif
-__device__ FE_EPI_INLINE void segment_epilogue(const EpilogueParams p, uint32_t tmem_base, uint32_t bar_tmem_full, uint32_t bar_tmem_empty,
+__device__ __noinline__ void segment_epilogue(const EpilogueParams p, uint32_t tmem_base, uint32_t bar_tmem_full, uint32_t bar_tmem_empty,
                                           int* arrivals_s, uint32_t parity, int stages_here, int tile, bool whole_tile,
                                           bool first_segment) {
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127;
@@ -218,8 +216,9 @@ __device__ FE_EPI_INLINE void segment_epilogue(const EpilogueParams p, uint32_t 
     for (int j = 0; j < 32; ++j) sum[j] = 0.f;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     // the partial sums are added smallest first (accumulator 0 holds the lo terms), in fp32 round-to-nearest
-    const int n_acc = 1 + rotation(stages_here);                   // short segments use fewer than 16
-    for (int a = 0; a < n_acc; ++a) {
+    const int n_acc = 1 + rotation(stages_here);                   // per issuer; short segments use fewer than 8
+    for (int ai = 0; ai < kIssuers * n_acc; ++ai) {
+        const int a = (ai % kIssuers) * (kAccs / kIssuers) + ai / kIssuers;   // 0, 8 (the lo terms), 1, 9, 2, 10, ...
         uint32_t v[32];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -307,9 +306,9 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), kProducerThreads / 32); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int s = 0; s < kBStages; ++s) { mbar_init(smem_u32(&bar_bfull[s]), 1); mbar_init(smem_u32(&bar_bempty[s]), 1); }
-        mbar_init(smem_u32(&bar_tmem_full), 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), kProducerThreads / 32); mbar_init(smem_u32(&bar_empty[s]), kIssuers); }
+        for (int s = 0; s < kBStages; ++s) { mbar_init(smem_u32(&bar_bfull[s]), 1); mbar_init(smem_u32(&bar_bempty[s]), kIssuers); }
+        mbar_init(smem_u32(&bar_tmem_full), kIssuers);
         mbar_init(smem_u32(&bar_tmem_empty), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -434,22 +433,15 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                         }
 #pragma unroll
                         for (int px = 0; px < 8; ++px) {                       // (padding pixels meet zero weights: no masking)
-#ifdef FE_DIAG_NOEPI
-                            hi[og][px] = __float_as_uint(acc[px]) & 0xffffe000u; lo[og][px] = 0u;
-#else
                             const float a = fmaxf(acc[px], acc[px] * p.slope); // LeakyReLU for 0 <= slope <= 1 (checked at create)
                             hi[og][px] = to_tf32(a);                           // round-to-nearest tf32: exactly what the tensor core will read
                             lo[og][px] = __float_as_uint(a - __uint_as_float(hi[og][px]));   // exact in fp32, |lo| <= 2^-11 |a|; the tensor core keeps its top 10 bits
-#endif
                         }
                     }
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);               // the MMAs that read this slot have completed
                     uint8_t* a_hi = smem + s * kAStageBytes + (r >> 3) * kASbo + (r & 7) * 16 + strip * 256;
                     uint8_t* a_lo = a_hi + kABytes;
-#ifdef FE_DIAG_NOSTS
-                    if (hi[0][0] == 0x12345u && lo[kG - 1][7] == 0x54321u)
-#endif
 #pragma unroll
                     for (int og = 0; og < kG; ++og) {                          // k' = og * 16 + strip * 8 + px -> core (k' / 4), 128 B apart
                         *reinterpret_cast<uint4*>(a_hi + og * 512) = make_uint4(hi[og][0], hi[og][1], hi[og][2], hi[og][3]);
@@ -468,8 +460,10 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                 segment_epilogue(p.epi, tmem_base, smem_u32(&bar_tmem_full), smem_u32(&bar_tmem_empty), &arrivals_s, item_n & 1u, stages_here,
                                  tile, c_end - c_begin == p.n_chunks, first_segment);
         }
-    } else if (warp == 8) {
-        // ---------------------------------------------------------------------- MMA issuer (one elected lane)
+    } else if (warp != 9) {
+        // ---------------------------------------------------------------------- MMA issuers (warps 8 and 10, one elected lane each)
+        // Issuer w takes the K steps ks = w, w + 2, w + 4 of every stage and owns accumulators 8 w .. 8 w + 7.
+        const uint32_t w = warp == 8 ? 0u : 1u;
         // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 32, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kFeat >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
         const uint32_t elected = elect_one();
@@ -486,7 +480,8 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
             // number of MMAs chained on one accumulator: the hi*hi steps rotate over up to 15 accumulators, the (2^-11 smaller)
             // lo terms have their own; the epilogue adds the partial sums
             const uint32_t n_rot = (uint32_t)rotation(stages_here);
-            uint32_t acc = 1;
+            const uint32_t acc_lo = w * (kAccs / kIssuers);
+            uint32_t acc = acc_lo + 1;
             for (int st = 0; st < stages_here; ++st, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                 const uint32_t sb = it % kBStages, phb = (it / kBStages) & 1u;
@@ -494,20 +489,21 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
                 mbar_wait(smem_u32(&bar_full[s]), ph);                         // activations written by the 256 producers
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_base + s * kAStageBytes, b_hi = smem_base + kStages * kAStageBytes + sb * kBStageBytes;
-                uint64_t dah = umma_desc(a_hi, 128, kASbo), dal = umma_desc(a_hi + kABytes, 128, kASbo);
-                uint64_t dbh = umma_desc(b_hi, 128, kBSbo), dbl = umma_desc(b_hi + kBBytes, 128, kBSbo);
+                uint64_t dah = umma_desc(a_hi + w * 256, 128, kASbo), dal = umma_desc(a_hi + kABytes + w * 256, 128, kASbo);
+                uint64_t dbh = umma_desc(b_hi + w * 256, 128, kBSbo), dbl = umma_desc(b_hi + kBBytes + w * 256, 128, kBSbo);
 #pragma unroll
-                for (int ks = 0; ks < kStageK / 8; ++ks) {                     // one K=8 step = two 16-byte cores, 256 B further on
+                for (int kk = 0; kk < kStageK / 8 / kIssuers; ++kk) {          // one K=8 step = two 16-byte cores, 256 B further on
 #ifndef FE_DIAG_NOMMA
                     umma_tf32(tmem_base + acc * kFeat, dah, dbh, idesc, (used >> acc) & 1u, elected);
 #endif
 #if !defined(FE_DIAG_HIONLY) && !defined(FE_DIAG_NOMMA)                        // diagnostic build: one MMA per K step instead of three
-                    umma_tf32(tmem_base, dal, dbh, idesc, used & 1u, elected);
-                    umma_tf32(tmem_base, dah, dbl, idesc, 1u, elected);
+                    umma_tf32(tmem_base + acc_lo * kFeat, dal, dbh, idesc, (used >> acc_lo) & 1u, elected);
+                    umma_tf32(tmem_base + acc_lo * kFeat, dah, dbl, idesc, 1u, elected);
 #endif
-                    used |= 1u | (1u << acc);
-                    acc = acc == n_rot ? 1u : acc + 1u;
-                    dah += 256 >> 4; dal += 256 >> 4; dbh += 256 >> 4; dbl += 256 >> 4;   // the address field counts 16-byte units
+                    used |= (1u << acc_lo) | (1u << acc);
+                    acc = acc == acc_lo + n_rot ? acc_lo + 1u : acc + 1u;
+                    dah += kIssuers * 256 >> 4; dal += kIssuers * 256 >> 4;    // the address field counts 16-byte units
+                    dbh += kIssuers * 256 >> 4; dbl += kIssuers * 256 >> 4;
                 }
                 umma_commit(smem_u32(&bar_empty[s]), elected);                 // frees both slots when these MMAs have read them
                 umma_commit(smem_u32(&bar_bempty[sb]), elected);

@@ -9,10 +9,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "w0_cur": [],
-    "w1_rotfixed": ["-DFE_ROT_FIXED"],
-    "w2_nomma": ["-DFE_DIAG_NOMMA"],
-    "w3_inline": ["-DFE_INLINE_EPI"],
+    "x0_cur": [],
+    "x1_nomma": ["-DFE_DIAG_NOMMA"],
 }
 
 if sys.argv[1:] == ["build"]:
