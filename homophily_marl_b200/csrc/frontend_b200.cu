@@ -348,31 +348,38 @@ obs_frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant
             const long long row_ld = row < p.epi.rows ? row : p.epi.rows - 1;          // partial last tile: compute on a valid row, never store
             const uint8_t* view = p.obs + row_ld * p.AS;
             uint32_t win[3][9], nxt[9];
-            auto load_row = [&](uint32_t (&dst)[9], int yy, int xb) {
-                const int x0 = xb * 16 + strip * 8;
+            // src points at (row yy, pixel x0) of plane 0; the three guards depend on the column only
+            auto load_row = [&](uint32_t (&dst)[9], const uint8_t* src, bool g0, bool g1, bool g2) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const uint8_t* src = view + ch * p.PS + yy * p.RP + x0;
+                for (int ch = 0; ch < 3; ++ch, src += p.PS) {
 #ifdef FE_DIAG_NOLOAD                                                  // diagnostic build: one load per row instead of 9
                     if (ch == 0) dst[0] = __ldg(reinterpret_cast<const uint32_t*>(src));
                     dst[ch * 3] = dst[0] + ch; dst[ch * 3 + 1] = dst[0] ^ ch; dst[ch * 3 + 2] = dst[0] + 3 * ch;
 #else
-                    dst[ch * 3] = x0 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
-                    dst[ch * 3 + 1] = x0 + 4 < p.RP ? __ldg(reinterpret_cast<const uint32_t*>(src + 4)) : 0u;
-                    dst[ch * 3 + 2] = x0 + 8 < p.N ? __ldg(reinterpret_cast<const uint32_t*>(src + 8)) : 0u;   // only pixels x0+8, x0+9 < N are used
+                    dst[ch * 3] = g0 ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
+                    dst[ch * 3 + 1] = g1 ? __ldg(reinterpret_cast<const uint32_t*>(src + 4)) : 0u;
+                    dst[ch * 3 + 2] = g2 ? __ldg(reinterpret_cast<const uint32_t*>(src + 8)) : 0u;   // only pixels x0+8, x0+9 < N are used
 #endif
                 }
             };
+            int xb = c_begin / p.P, y = c_begin - xb * p.P;                    // kept incrementally: no division per chunk
+            const uint8_t* next_row = view;                                    // row y + 3 of the current column, at pixel x0
+            bool g0 = false, g1 = false, g2 = false;
             for (int c = c_begin; c < c_end; ++c) {
-                const int xb = c / p.P, y = c - xb * p.P;
                 if (c == c_begin || y == 0) {                                  // first chunk of the item or of a column: whole window
-                    load_row(win[0], y, xb);
-                    load_row(win[1], y + 1, xb);
-                    load_row(nxt, y + 2, xb);
+                    const int x0 = xb * 16 + strip * 8;
+                    g0 = x0 < p.RP; g1 = x0 + 4 < p.RP; g2 = x0 + 8 < p.N;
+                    const uint8_t* src = view + y * p.RP + x0;
+                    load_row(win[0], src, g0, g1, g2);
+                    load_row(win[1], src + p.RP, g0, g1, g2);
+                    load_row(nxt, src + 2 * p.RP, g0, g1, g2);
+                    next_row = src + 3 * p.RP;
                 }
 #pragma unroll
                 for (int k = 0; k < 9; ++k) win[2][k] = nxt[k];
-                if (c + 1 < c_end && y + 1 < p.P) load_row(nxt, y + 3, xb);    // the row the next chunk adds
+                if (c + 1 < c_end && y + 1 < p.P) load_row(nxt, next_row, g0, g1, g2);   // the row the next chunk adds
+                next_row += p.RP;
+                if (++y == p.P) { y = 0; ++xb; }
                 uint32_t cur[27];
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)

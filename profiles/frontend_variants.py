@@ -9,8 +9,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "x0_cur": [],
-    "x1_nomma": ["-DFE_DIAG_NOMMA"],
+    "g3_s2_b4": [],
+    "g3_s3_b4": ["-DFE_STAGES=3"],
+    "g2_s3_b6": ["-DFE_OC_PER_STAGE=2", "-DFE_STAGES=3", "-DFE_BSTAGES=6"],
+    "g2_s4_b6": ["-DFE_OC_PER_STAGE=2", "-DFE_STAGES=4", "-DFE_BSTAGES=6"],
+    "g2_s6_b8": ["-DFE_OC_PER_STAGE=2", "-DFE_STAGES=6", "-DFE_BSTAGES=8"],
+    "g1_s6_b12": ["-DFE_OC_PER_STAGE=1", "-DFE_STAGES=6", "-DFE_BSTAGES=12"],
+    "g1_s12_b16": ["-DFE_OC_PER_STAGE=1", "-DFE_STAGES=12", "-DFE_BSTAGES=16"],
 }
 
 if sys.argv[1:] == ["build"]:
