@@ -4,7 +4,7 @@
 
 Tolerance (stated, not hidden): the reference computes in fp32.  The kernel's conv is fp32 FMA; the Linear contraction runs
 on tf32 tensor cores with both operands split hi + lo (hi*hi + lo*hi + hi*lo), accumulated in fp32 over 16 TMEM accumulators
-and split-K partial sums.  Against an fp64 evaluation of the same module the kernel must be within 1e-6 * (1 + |y|) -- measured
+and per-CTA partial sums of shared tiles.  Against an fp64 evaluation of the same module the kernel must be within 1e-6 * (1 + |y|) -- measured
 0.3e-7 .. 1.2e-7, torch's own fp32 path measures 0.5e-7 .. 1.0e-6 on the same inputs -- and within 3e-6 * (1 + |y|) of torch
 fp32 on the GPU (TF32 disabled in cuDNN / cuBLAS for the comparison)."""
 import numpy as np
