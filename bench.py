@@ -463,6 +463,11 @@ class DeviceRollout:
         self.env.close()
 
 
+def auto_groups(B):
+    """Env ranges per step: small batches are stepped as 8 (4) independent ranges on as many streams (SSDBatchEnv.step_range)."""
+    return 8 if (B <= 4096 and B % 8 == 0) else (4 if (B <= 8192 and B % 4 == 0) else 1)
+
+
 def measure(cfg, a, dev, rank, world, K, warmup, replays, groups=1, clock=None, dist=None):
     """Warm-up, one untimed pass over every graph of the schedule, then `replays` individually timed K-step replays."""
     import torch
@@ -542,7 +547,7 @@ def run_b200(a):
     B, n = cfg["envs_per_gpu"], cfg["num_agents"]
     K, R = a.steps, auto_replays(a, a.steps)
     if a.groups <= 0:                                         # one wave of warps cannot overlap its own logic and store phases
-        a.groups = 8 if (B <= 4096 and B % 8 == 0) else (4 if (B <= 8192 and B % 4 == 0) else 1)
+        a.groups = auto_groups(B)
     single = None
     if a.groups > 1:                                          # the same K steps as ONE launch per step, for the record
         r1, ro1 = measure(cfg, a, dev, rank, world, K, a.warmup, max(5, R // 4), groups=1, dist=dist)
@@ -595,7 +600,8 @@ def run_b200(a):
                 lo, hi = shard_range(WORKLOADS[name][4], rank, world)
                 c2["envs_per_gpu"], c2["global_envs"], c2["gid_base"] = hi - lo, WORKLOADS[name][4], lo
             try:
-                r2, ro2 = measure(c2, a, dev, rank, world, LIMIT, 5, 7, dist=dist)
+                g2 = auto_groups(c2["envs_per_gpu"])
+                r2, ro2 = measure(c2, a, dev, rank, world, LIMIT, 5, 7, groups=g2, dist=dist)
                 ro2.close()
                 del ro2
                 torch.cuda.empty_cache()
@@ -604,7 +610,7 @@ def run_b200(a):
                 ach = r2["alg_bytes"] / (r2["ms_per_step"] * 1e-3) / 1e9
                 extra[name] = {"value": r2["value"], "us_per_step": r2["ms_per_step"] * 1e3, "frac": ach / peak, "achieved_gbs_per_gpu": ach,
                                "envs_per_gpu": c2["envs_per_gpu"], "global_envs": c2["global_envs"], "scaling": scaling,
-                               "what": WORKLOADS[name][5], "replay_ms": r2["replay_ms"]}
+                               "env_ranges": g2, "what": WORKLOADS[name][5], "replay_ms": r2["replay_ms"]}
             except Exception as e:
                 extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
 

@@ -63,6 +63,7 @@ struct MapDev {
 struct KParams {
     int kind, B, n, H, W, G, V, N;
     int env0, env1;                           // this launch covers env instances [env0, env1) of the B resident ones
+    int pdl;                                  // launched with the programmatic-serialization attribute (set per launch)
     int GS, NA, RP, PS, AS, ES;               // strides (ssd_layout)
     int pitchM, pitchT, off_map[4], PMS;      // nibble maps M / MT: row pitches, byte offset by orientation (0,1 -> MT; 2,3 -> M), total bytes
     int direct, padF, padB;                   // direct-gather render (small views): slack bytes before / after the staged grid
@@ -905,6 +906,22 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
     // start a fresh CTA whenever one retires decorrelates the phases; profiles/r2_notes.md.)
     const int env = p.env0 + (blockIdx.x * kWarps + warp) * SW::kEnvs + w.sub;
     if (env >= p.env1) return;
+    // Prologue that touches nothing an earlier launch writes (colour LUT, slack / "outside" fill of the staging tile).  Under
+    // programmatic dependent launch (small launches, p.pdl) it runs first, while the previous launch of the stream is still
+    // storing observations, and the state loads follow the grid dependency; otherwise it runs under the state loads.
+    auto prologue = [&]() {
+        if (lane < 16) lut_s[lane] = p.lut[lane];             // (made visible by w.sync below)
+        if (p.obs) {
+            if (g.direct()) {                                 // zero the slack around the grid (read, then masked, by the gather)
+                for (int i = lane; i < (g.padF() >> 4); i += SW::kLanes) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
+                for (int i = lane; i < (g.padB() >> 4); i += SW::kLanes) reinterpret_cast<uint4*>(sg + g.GS())[i] = make_uint4(0, 0, 0, 0);
+            } else fill_outside(w, g, p, pmap, lane);         // "outside the map"
+        }
+    };
+    if (p.pdl) {
+        prologue();
+        asm volatile("griddepcontrol.wait;" ::: "memory");    // the previous launch of the stream has completed, its writes are visible
+    }
     {
         if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
         const uint32_t gid = p.gid_base + (uint32_t)env;
@@ -925,13 +942,7 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
                                                   : reinterpret_cast<const uint4*>(p.grid + (size_t)env * g.GS());
             uint4 g0 = make_uint4(0, 0, 0, 0);
             if (lane < n16) g0 = src[lane];
-            if (lane < 16) lut_s[lane] = p.lut[lane];         // while the state loads are in flight (made visible by w.sync below)
-            if (p.obs) {
-                if (g.direct()) {                             // zero the slack around the grid (read, then masked, by the gather)
-                    for (int i = lane; i < (g.padF() >> 4); i += SW::kLanes) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0, 0, 0, 0);
-                    for (int i = lane; i < (g.padB() >> 4); i += SW::kLanes) reinterpret_cast<uint4*>(sg + g.GS())[i] = make_uint4(0, 0, 0, 0);
-                } else fill_outside(w, g, p, pmap, lane);     // "outside the map"
-            }
+            if (!p.pdl) prologue();                           // while the state loads are in flight
             if (lane < n16) reinterpret_cast<uint4*>(sg)[lane] = g0;
             for (int i = lane + SW::kLanes; i < n16; i += SW::kLanes) reinterpret_cast<uint4*>(sg)[i] = src[i];
         }
@@ -1006,6 +1017,9 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
             if (lane == 0) { p.t[env] = 0; p.tick[env] = tick + 1; p.counts[env] = (uint32_t)apples | ((uint32_t)waste << 16); }
         }
 
+        // the next launch of this stream may become resident now (its prologue overlaps this launch's stores; it still waits
+        // for this whole grid before it reads any state)
+        if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (MODE != MODE_RENDER) {                                 // strip the occupancy bits, write the state back
             if (is_agent && lane == __ffs(same) - 1) sg[pos] &= 0x7f;
             w.sync();
@@ -1088,6 +1102,7 @@ struct ssd_handle {
     size_t smem_bytes;
     int64_t launches;
     int force_generic;                                        // SSD_B200_GENERIC=1: always use the runtime-geometry kernels
+    int pdl;                                                  // programmatic dependent launch for small launches (SSD_B200_PDL=0 turns it off)
     int lanes_per_env;                                        // 16: two envs per warp (needs <= 16 spawn points); 32: one
 };
 
@@ -1124,14 +1139,33 @@ static int launch_lpe(ssd_handle* h, const KParams& k, void* stream) {
     int grid = (k.env1 - k.env0 + envs_per_cta - 1) / envs_per_cta;
     if (grid <= 0) return SSD_OK;
 
-    ssd_kernel<MODE, GEO, LPE><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
+    if (k.pdl) {                                               // programmatic dependent launch (see launch_geo)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kWarps * 32); cfg.dynamicSmemBytes = h->smem_bytes;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SSD_CUDA(cudaLaunchKernelEx(&cfg, ssd_kernel<MODE, GEO, LPE>, k));
+    } else {
+        ssd_kernel<MODE, GEO, LPE><<<grid, kWarps * 32, h->smem_bytes, (cudaStream_t)stream>>>(k);
+    }
     ++h->launches;
     SSD_CUDA(cudaGetLastError());
     return SSD_OK;
 }
 
+// Launches of at most a few waves are bound by the latency of their own chain (launch -> state loads -> logic -> stores), so
+// consecutive launches of a stream are chained programmatically: the next one becomes resident and runs its prologue while this
+// one stores observations (cleanup5, 4 096 envs in 8 ranges: 8.7 -> 7.2 us per step; harvest5: 12.1 -> 10.2 us).  Large
+// launches gain nothing and pay for the prologue no longer running under the state loads, so they keep the plain launch.
+constexpr int kPdlMaxEnvs = 2048;
+
 template <int MODE, class GEO>
-static int launch_geo(ssd_handle* h, const KParams& k, void* stream) {
+static int launch_geo(ssd_handle* h, const KParams& k_in, void* stream) {
+    KParams k = k_in;
+    k.pdl = h->pdl && (k.env1 - k.env0) <= kPdlMaxEnvs;
 #ifdef SSD_ENABLE_LPE16                                        // experiment: two envs per warp (measured slower, profiles/r1_notes.md)
     if (h->lanes_per_env == 16) return launch_lpe<MODE, GEO, 16>(h, k, stream);
 #endif
@@ -1261,6 +1295,7 @@ int ssd_create(const ssd_config* cfg, ssd_handle** out) {
 #endif
     h->smem_bytes = (size_t)kWarps * (32 / h->lanes_per_env) * k.smem_per_warp;
     { const char* e = getenv("SSD_B200_GENERIC"); h->force_generic = e && e[0] == '1'; }
+    { const char* e = getenv("SSD_B200_PDL"); h->pdl = !(e && e[0] == '0'); }
     h->device = cfg->device;
 
     DeviceGuard guard(cfg->device);
