@@ -15,6 +15,9 @@
  * code and never throws; no internal threads; calls on one handle must be
  * serialised by the caller (except ssd_step_range on disjoint ranges).  There is no CPU fallback: without a CUDA device
  * ssd_create fails with SSD_ERR_CUDA.
+ * Launches of at most 2048 envs are chained to the preceding kernel of `stream` by programmatic dependent launch: their
+ * CTAs may become resident early, but they read nothing before all earlier work of the stream has completed, so stream
+ * order holds exactly as for a plain launch (environment variable SSD_B200_PDL=0 disables it).
  */
 #ifndef SSD_B200_H
 #define SSD_B200_H
