@@ -464,8 +464,14 @@ class DeviceRollout:
 
 
 def auto_groups(B):
-    """Env ranges per step: small batches are stepped as 8 (4) independent ranges on as many streams (SSDBatchEnv.step_range)."""
-    return 8 if (B <= 4096 and B % 8 == 0) else (4 if (B <= 8192 and B % 4 == 0) else 1)
+    """Env ranges per step (SSDBatchEnv.step_range, one stream each): up to 4 096 envs as 8 ranges, up to 16 384 as ranges of 2 048
+    (the largest launch that is chained by programmatic dependent launch); larger batches as one launch -- measured optimum in
+    each regime (profiles/r2_notes.md sections 2-3)."""
+    if B <= 4096 and B % 8 == 0:
+        return 8
+    if B <= 16384 and B % 2048 == 0:
+        return B // 2048
+    return 1
 
 
 def measure(cfg, a, dev, rank, world, K, warmup, replays, groups=1, clock=None, dist=None):
