@@ -64,3 +64,14 @@ def test_cuda_arm_line():
     assert d["replays"] >= 5 and d["replay_ms"]["min"] <= d["replay_ms"]["median"] <= d["replay_ms"]["max"]
     assert "l2" not in d["config"] and "parallelism" not in d["config"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_env_range_rule():
+    """Small batches are stepped as env ranges (profiles/r2_notes.md sections 2-3); every range size must divide the batch."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert [bench.auto_groups(b) for b in (512, 2048, 4096, 8192, 16384, 65536, 4095, 10000)] == [8, 8, 8, 4, 8, 1, 1, 1]
+    for b in (512, 2048, 4096, 8192, 16384):
+        assert b % bench.auto_groups(b) == 0
