@@ -923,28 +923,30 @@ __global__ void __launch_bounds__(kWarps * 32, SSD_MIN_BLOCKS) ssd_kernel(const 
         asm volatile("griddepcontrol.wait;" ::: "memory");    // the previous launch of the stream has completed, its writes are visible
     }
     {
-        if (MODE == MODE_RESET && p.mask && p.mask[env] == 0) return;
+        if (MODE == MODE_RESET && p.mask && __ldcg(p.mask + env) == 0) return;
         const uint32_t gid = p.gid_base + (uint32_t)env;
-        // every global load of the step is issued up front
-        const uint32_t tick = p.tick[env];
-        const int t_prev = MODE == MODE_STEP ? p.t[env] : 0;
-        const uint32_t cnt = MODE == MODE_STEP ? p.counts[env] : 0u;
-        const int act = (MODE == MODE_STEP && is_agent) ? (int)p.actions[(size_t)env * p.n + lane] : 255;
+        // every global load of the step is issued up front.  Mutable state is read past L1 (ld.global.cg): each entry is read once
+        // per step anyway, and a launch that became resident before its predecessors finished (programmatic dependent launch,
+        // concurrent env ranges sharing a cache line at a range boundary) must never see a line an earlier CTA left in this SM's L1.
+        const uint32_t tick = __ldcg(p.tick + env);
+        const int t_prev = MODE == MODE_STEP ? __ldcg(p.t + env) : 0;
+        const uint32_t cnt = MODE == MODE_STEP ? __ldcg(p.counts + env) : 0u;
+        const int act = (MODE == MODE_STEP && is_agent) ? (int)__ldcg(p.actions + (size_t)env * p.n + lane) : 255;
         int pos = -1 - lane, ori = 0, ep_ret = 0;
         uint32_t a_rec = 0;
         if (MODE != MODE_RESET && is_agent) {
-            a_rec = p.agent[(size_t)env * p.NA + lane];
-            ep_ret = p.ep_ret[(size_t)env * p.NA + lane];
+            a_rec = __ldcg(p.agent + (size_t)env * p.NA + lane);
+            ep_ret = __ldcg(p.ep_ret + (size_t)env * p.NA + lane);
         }
         const int n16 = g.GS() >> 4;
         {
             const uint4* src = MODE == MODE_RESET ? reinterpret_cast<const uint4*>(p.map->base_grid)
                                                   : reinterpret_cast<const uint4*>(p.grid + (size_t)env * g.GS());
             uint4 g0 = make_uint4(0, 0, 0, 0);
-            if (lane < n16) g0 = src[lane];
+            if (lane < n16) g0 = __ldcg(src + lane);
             if (!p.pdl) prologue();                           // while the state loads are in flight
             if (lane < n16) reinterpret_cast<uint4*>(sg)[lane] = g0;
-            for (int i = lane + SW::kLanes; i < n16; i += SW::kLanes) reinterpret_cast<uint4*>(sg)[i] = src[i];
+            for (int i = lane + SW::kLanes; i < n16; i += SW::kLanes) reinterpret_cast<uint4*>(sg)[i] = __ldcg(src + i);
         }
         if (MODE != MODE_RESET && is_agent) {
             pos = (int)(a_rec & 0xff) * g.W() + (int)((a_rec >> 8) & 0xff);
