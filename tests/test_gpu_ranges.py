@@ -9,12 +9,15 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-@pytest.mark.parametrize("name,mp,n,view,groups", [("harvest", "default5", 5, 15, 4), ("cleanup", "default10", 10, 7, 3)])
-def test_groups_on_streams_equal_one_batch(name, mp, n, view, groups):
+@pytest.mark.parametrize("name,mp,n,view,groups,per", [("harvest", "default5", 5, 15, 4, 96), ("cleanup", "default10", 10, 7, 3, 96),
+                                                         ("cleanup", "default5", 5, 7, 3, 40), ("harvest", "default5", 5, 15, 5, 23)])
+def test_groups_on_streams_equal_one_batch(name, mp, n, view, groups, per):
     """G disjoint env ranges stepped concurrently on G streams (each at its own pace) == the same envs stepped as one batch:
-    draws are keyed by the global env id, so the split is invisible."""
+    draws are keyed by the global env id, so the split is invisible.  The launches of a range are chained by programmatic
+    dependent launch and overlap those of the other ranges; ranges of 40 / 23 envs share cache lines of the state arrays at
+    their boundaries."""
     from homophily_marl_b200.batch_env import SSDBatchEnv
-    B, T = 96 * groups, 23
+    B, T = per * groups, 23
     extra = dict(random_spawn_point=True, random_spawn_rotation=None)
     kw = dict(map=mp, view_size=view, episode_limit=1000, extra_args=extra, seed=9, env_gid_base=100)
     one = SSDBatchEnv(name, B, n, **kw)
