@@ -8,7 +8,7 @@ from collections import Counter
 lib = sys.argv[1] if len(sys.argv) > 1 else "homophily_marl_b200/libssd_b200.so"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "STG.E.ENL2.256", "STG.E.128", "LDG.E.128", "FFMA2",
-       "PRMT", "SHF", "LOP3", "MATCH", "VOTE", "REDUX", "CREDUX", "SHFL", "ATOMS", "LDS", "STS", "FFMA", "IMAD", "HMMA", "F2FP", "BAR")
+       "ACQBULK", "PREEXIT", "PRMT", "SHF", "LOP3", "MATCH", "VOTE", "REDUX", "CREDUX", "SHFL", "ATOMS", "LDS", "STS", "FFMA", "IMAD", "HMMA", "F2FP", "BAR")
 fn, counts, arch = None, {}, None
 for line in out.splitlines():
     m = re.search(r"arch = (sm_\w+)", line)
